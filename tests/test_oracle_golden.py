@@ -1,0 +1,97 @@
+"""Pin oracle/rn_oracle.py to the reference: every fixture in tests/golden/ was produced by the
+unmodified reference model.py (tests/golden/make_golden.py).  CPU only."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import rn_oracle as O
+from tests.golden_util import CASES, case_inputs, case_params, golden_grad_check, load_npz
+
+TOL = 2e-5      # fp32 vs fp32, different summation order only
+
+EVAL_CASES = [s for s in CASES]
+TRAIN_CASES = [s for s in CASES if s != "seeded_original_fp_d12"]
+
+
+@pytest.mark.parametrize("stem", EVAL_CASES)
+def test_eval_forward_matches_reference(stem):
+    z = load_npz(stem + "_eval")
+    hyp, p = case_params(stem)
+    img, qst = case_inputs(z)
+    logp, parts = O.rn_forward(p, hyp, img, qst, training=False, return_parts=True)
+    assert O.rel_err(parts["q"], torch.from_numpy(z["q"])) < TOL
+    if parts["feat"] is not None:
+        assert O.rel_err(parts["feat"], torch.from_numpy(z["feat"])) < TOL
+    assert O.rel_err(parts["x_g"], torch.from_numpy(z["x_g"])) < TOL
+    assert O.rel_err(logp, torch.from_numpy(z["logp"])) < TOL
+
+
+@pytest.mark.parametrize("stem", TRAIN_CASES)
+def test_train_step_matches_reference(stem):
+    z = load_npz(stem + "_train")
+    hyp, p = case_params(stem)
+    img, qst = case_inputs(z)
+    label = torch.from_numpy(z["label"])
+    mask = torch.from_numpy(z["dropout_mask"])
+    leaves = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in p.items()}
+    running = {}
+    logp = O.rn_forward(leaves, hyp, img, qst, training=True, dropout_mask=mask, running_out=running)
+    loss = F.nll_loss(logp, label)
+    loss.backward()
+    assert O.rel_err(logp.detach(), torch.from_numpy(z["logp"])) < TOL
+    assert abs(float(loss.detach()) - float(z["loss"])) < TOL * max(1.0, abs(float(z["loss"])))
+    errs = {}
+    n = 0
+    for k, v in leaves.items():
+        if f"grad/{k}/l2" in z.files:
+            golden_grad_check(z, k, v.grad, 3e-4, errs)   # fp32 vs fp32 through 4 BN layers
+            n += 1
+    assert n >= (19 if hyp["state_description"] else 35)
+    for k, v in running.items():
+        assert O.rel_err(v, torch.from_numpy(z["running/" + k])) < TOL
+
+
+@pytest.mark.parametrize("stem", ["seeded_original_fp", "seeded_ir_fp", "seeded_original_sd", "seeded_ir_sd"])
+def test_factorised_equals_dense_fp64(stem):
+    """The factorised form (what the kernels compute) is the same function as the literal one,
+    forward and backward, to fp64 round-off."""
+    config = CASES[stem][0]
+    hyp = O.HYPERPARAMS[config]
+    p = O.seeded_params(hyp, 82, 28, 7, torch.float64)
+    n, k = (12, 7) if hyp["state_description"] else (16, 26)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, n, k, generator=g, dtype=torch.float64, requires_grad=True)
+    q = torch.randn(3, hyp["lstm_hidden"], generator=g, dtype=torch.float64, requires_grad=True)
+    gp = [(w.clone().requires_grad_(True), b.clone().requires_grad_(True)) for w, b in O.g_layer_params(p, 4)]
+    qinj = hyp["question_injection_position"]
+    xg_dense = O.g_mlp_dense(x, q, gp, qinj)
+    xg_fact, saved = O.g_mlp_factorised(x, q, gp, qinj)
+    assert O.rel_err(xg_fact, xg_dense) < 1e-12
+    dxg = torch.randn(xg_dense.shape, generator=g, dtype=torch.float64)
+    xg_dense.backward(dxg)
+    with torch.no_grad():
+        out = O.g_backward_factorised(x, q, gp, qinj, saved, dxg)
+    assert O.rel_err(out["dx"], x.grad) < 1e-11
+    assert O.rel_err(out["dq"], q.grad) < 1e-11
+    for l, (w, b) in enumerate(gp):
+        assert O.rel_err(out["dW"][l], w.grad) < 1e-11, l
+        assert O.rel_err(out["db"][l], b.grad) < 1e-11, l
+
+
+def test_clip_and_adam_matches_torch():
+    torch.manual_seed(0)
+    ws = [torch.randn(5, 7), torch.randn(11)]
+    gs = [torch.randn(5, 7) * 30, torch.randn(11) * 30]
+    ref = [w.clone().requires_grad_(True) for w in ws]
+    opt = torch.optim.Adam(ref, lr=5e-3, weight_decay=1e-4)
+    mine = [w.clone() for w in ws]
+    m = [torch.zeros_like(w) for w in ws]
+    v = [torch.zeros_like(w) for w in ws]
+    for step in range(1, 4):
+        for r, g in zip(ref, gs):
+            r.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(ref, 50.0)
+        opt.step()
+        O.clip_and_adam(mine, [g.clone() for g in gs], m, v, step, lr=5e-3)
+        for a, b in zip(mine, ref):
+            assert torch.allclose(a, b.detach(), rtol=1e-5, atol=1e-6)
