@@ -1,0 +1,181 @@
+/*
+ * rn_b200.h -- C ABI of librn_b200.so: the B200 (sm_100a) Relation-Network hot path.
+ *
+ * The reference (mesnico/RelationNetworks-CLEVR) is pure Python/PyTorch and has no FFI of
+ * its own; the interface each entry point replaces is a span of reference `model.py`,
+ * cited per function below.  The host side (relationnetworks_clevr_b200/ops.py) binds these
+ * with ctypes -- see INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, a negative RN_ERR_* code otherwise; a human
+ *     readable message for the calling thread is available from rn_last_error().
+ *   - All pointers are DEVICE pointers unless the name starts with `h_`.  The caller owns all
+ *     memory: inputs, outputs, `saved` (activations kept from forward for backward) and
+ *     `scratch` (dead after the call returns its work to the stream).  The library never
+ *     allocates or frees device memory and keeps no pointer after a call returns.
+ *   - All tensors are contiguous, row-major, fp32 unless stated.  `stream` is a cudaStream_t
+ *     passed as void*.  Calls are asynchronous on that stream, never synchronise the device,
+ *     and are CUDA-graph capturable.
+ *   - Buffers must be 16-byte aligned (256-byte for `saved` and `scratch`).
+ */
+#ifndef RN_B200_H_
+#define RN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RN_ABI_VERSION 1
+
+/* error codes */
+#define RN_OK 0
+#define RN_ERR_INVALID_ARG (-1)   /* bad shape / null pointer / misalignment */
+#define RN_ERR_UNSUPPORTED (-2)   /* shape or mode not supported by the requested kernel family */
+#define RN_ERR_CUDA (-3)          /* a CUDA runtime call or launch failed */
+#define RN_ERR_ARCH (-4)          /* device is not compute capability 10.x */
+
+/* arithmetic of the g-MLP layers 1..L-1 (layer 0 is always fp32) */
+#define RN_PRECISION_FP32 0    /* fp32 SIMT kernels, any shape; on-device yardstick                 */
+#define RN_PRECISION_PARITY 1  /* tcgen05: fp16 activations x (W_hi + W_lo) fp16 split, fp32 accum  */
+#define RN_PRECISION_FAST 2    /* tcgen05: fp16 activations x fp16 weights, one pass, fp32 accum    */
+
+#define RN_MAX_G_LAYERS 8
+
+/* Shape of one relation-layer call.  Mirrors RelationalLayer.__init__ (model.py:82-102) and
+ * the sizes RelationalLayer.forward reads from its inputs (model.py:108-109). */
+typedef struct rn_relation_cfg {
+  int32_t B;          /* samples in this call                                              */
+  int32_t n;          /* objects per sample (d*d cells, or 12 state-description rows)      */
+  int32_t k;          /* features per object (26 from pixels incl. coords, 7 for SD)       */
+  int32_t Q;          /* question embedding width (hyp["lstm_hidden"])                     */
+  int32_t G;          /* width of every g layer (hyp["g_layers"], all equal)               */
+  int32_t L;          /* number of g layers                                                */
+  int32_t qinj;       /* hyp["question_injection_position"], 0 <= qinj < L                 */
+  int32_t precision;  /* RN_PRECISION_*                                                    */
+  int32_t training;   /* 1: keep what rn_relation_bwd needs in `saved`                     */
+} rn_relation_cfg;
+
+int rn_abi_version(void);
+const char* rn_last_error(void);
+
+/* Number of kernels this library has launched in the calling process (monotonic; for bench accounting). */
+unsigned long long rn_launch_count(void);
+
+/* Returns RN_OK when `device` is a compute-capability 10.x GPU, RN_ERR_ARCH otherwise. */
+int rn_device_check(int device);
+
+/* 1 when the tcgen05 kernel family supports this shape (G == 256, n*n % 128 == 0, L == 4 ...). */
+int rn_relation_tc_supported(const rn_relation_cfg* cfg);
+
+/* Bytes of `saved` and `scratch` the forward/backward pair needs for this cfg. */
+int rn_relation_workspace(const rn_relation_cfg* cfg, size_t* saved_bytes, size_t* scratch_bytes);
+
+/*
+ * g-MLP over all n*n ordered pairs + pair-sum.  Replaces RelationalLayer.forward up to and
+ * including the `.sum(1)` (model.py:104-152):
+ *     row p = a*n + c of sample b is [x[b,c] | x[b,a] | q[b] at layer qinj]
+ *     x_g[b] = sum_p relu(W_{L-1} ... relu(W_0 row + b_0) ... + b_{L-1})
+ *   x    [B, n, k]      q  [B, Q]
+ *   g_w  h_ array of L device pointers, g_w[l] is [G, fan_in_l] exactly as
+ *        rl.g_layers.l.weight (fan_in_0 = 2k, +Q at l == qinj; fan_in_l = G otherwise)
+ *   g_b  h_ array of L device pointers to [G]
+ *   xg   [B, G] out
+ */
+int rn_relation_fwd(const rn_relation_cfg* cfg, const float* x, const float* q,
+                    const float* const* h_g_w, const float* const* h_g_b, float* xg,
+                    void* saved, void* scratch, void* stream);
+
+/*
+ * Backward of rn_relation_fwd (what autograd derives for model.py:104-152).
+ *   dxg [B, G] in;  dx [B, n, k], dq [B, Q] out (overwritten)
+ *   dg_w / dg_b: h_ arrays of L device pointers, same shapes as g_w / g_b, OVERWRITTEN with the
+ *   gradient summed over the batch.
+ */
+int rn_relation_bwd(const rn_relation_cfg* cfg, const float* dxg, const float* x, const float* q,
+                    const float* const* h_g_w, const void* saved, float* dx, float* dq,
+                    float* const* h_dg_w, float* const* h_dg_b, void* scratch, void* stream);
+
+/* ---- f-MLP head: fc1 -> ReLU -> fc2 -> Dropout -> ReLU -> fc3 -> log_softmax (model.py:155-162) ---- */
+typedef struct rn_f_cfg {
+  int32_t B;        /* samples */
+  int32_t G;        /* input width  (g_layers[-1]) */
+  int32_t F1;       /* hyp["f_fc1"] */
+  int32_t F2;       /* hyp["f_fc2"] */
+  int32_t A;        /* answers (adict_size) */
+  float keep_scale; /* 1/(1-p) applied where drop_mask != 0; ignored when drop_mask == NULL */
+} rn_f_cfg;
+
+/* saved: floats, B*(F1 + F2) (h1 and the post-dropout post-ReLU h2).  drop_mask: [B,F2] uint8 (0 = dropped)
+ * or NULL (eval / p == 0); the mask comes from the caller so the RNG stays the framework's (torch). */
+int rn_f_fwd(const rn_f_cfg* cfg, const float* xg, const float* w1, const float* b1, const float* w2,
+             const float* b2, const float* w3, const float* b3, const uint8_t* drop_mask, float* logp,
+             float* saved, void* stream);
+
+/* dlogp [B,A] in.  Outputs overwritten.  scratch: floats, B*(A + F2 + F1).  drop_mask only tells whether
+ * dropout was active (its contents are implied by saved h2 > 0). */
+int rn_f_bwd(const rn_f_cfg* cfg, const float* dlogp, const float* logp, const float* xg, const float* w1,
+             const float* w2, const float* w3, const uint8_t* drop_mask, const float* saved, float* dxg,
+             float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3, float* scratch,
+             void* stream);
+
+/* ---- conv feature extractor: 4 x [conv3x3 s2 p1 -> BatchNorm -> ReLU] + coords (model.py:22-36,192-201) ---- */
+#define RN_CONV_LAYERS 4
+#define RN_CONV_CH 24
+
+typedef struct rn_conv_cfg {
+  int32_t B;         /* images */
+  int32_t side;      /* input height == width, multiple of 16 */
+  int32_t training;  /* 1: batch statistics (+ running-stat update), 0: running statistics */
+  float eps;         /* BatchNorm eps (1e-5) */
+  float momentum;    /* BatchNorm momentum (0.1) */
+} rn_conv_cfg;
+
+/* Per-layer parameter block, host array of RN_CONV_LAYERS entries (device pointers inside). */
+typedef struct rn_conv_layer {
+  const float* w;        /* [24, cin, 3, 3], cin = 3 for layer 0 else 24 */
+  const float* bias;     /* [24] */
+  const float* gamma;    /* [24] BatchNorm weight */
+  const float* beta;     /* [24] BatchNorm bias */
+  float* running_mean;   /* [24] read in eval; updated in place in training */
+  float* running_var;    /* [24] */
+} rn_conv_layer;
+
+/* saved floats: raw conv outputs of all layers + 2*24 batch stats per layer; see rn_conv_workspace.
+ * objects out: [B, d*d, 26] with d = side/16 -- channels 0..23 the layer-4 activations, 24/25 the
+ * x/y coordinates linspace(-d/2, d/2, d) (model.py:208-213). */
+int rn_conv_workspace(const rn_conv_cfg* cfg, size_t* saved_floats, size_t* scratch_floats);
+int rn_conv_fwd(const rn_conv_cfg* cfg, const float* img, const rn_conv_layer* h_layers, float* objects,
+                float* saved, float* scratch, void* stream);
+
+typedef struct rn_conv_grads {
+  float* dw;      /* [24, cin, 3, 3] */
+  float* dbias;   /* [24] */
+  float* dgamma;  /* [24] */
+  float* dbeta;   /* [24] */
+} rn_conv_grads;
+
+/* dobjects [B, d*d, 26] in (coordinate columns ignored).  Gradients overwritten.  No image gradient
+ * (utils.py:135,143: images never require grad). */
+int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float* dobjects, const rn_conv_layer* h_layers,
+                const float* saved, const rn_conv_grads* h_grads, float* scratch, void* stream);
+
+/* ---- optimiser tail: clip_grad_norm + Adam with L2 weight decay (train.py:45-48,330) on flat buffers ---- */
+typedef struct rn_adam_cfg {
+  int64_t n;          /* elements in the flat parameter / gradient buffers */
+  float lr, beta1, beta2, eps, weight_decay;
+  float clip_norm;    /* <= 0 disables clipping */
+  float grad_scale;   /* gradients are multiplied by this first (1/world_size after an allreduce-sum) */
+  int32_t step;       /* 1-based Adam step */
+} rn_adam_cfg;
+
+/* norm_scratch: >= 1024 floats + 1.  total_norm_out (device, 1 float) receives the pre-clip norm. */
+int rn_clip_adam(const rn_adam_cfg* cfg, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                 float* norm_scratch, float* total_norm_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RN_B200_H_ */

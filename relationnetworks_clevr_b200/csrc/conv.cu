@@ -1,0 +1,562 @@
+// conv.cu -- the 4-layer feature extractor: 4 x [conv3x3 stride 2 pad 1 -> BatchNorm2d(24) -> ReLU]
+// followed by the (x, y) coordinate channels and the [B, n, 26] object layout
+// (reference model.py:9-36, 192-201, 208-213).
+//
+// Layout: NCHW fp32 like the reference.  The BatchNorm affine + ReLU of layer l is never written
+// out: conv l stores its RAW output y_l plus per-block partial sums (sum y, sum y^2); a finalize
+// kernel turns them into (mean, rstd, scale, shift), and conv l+1 applies relu(scale*y+shift) while
+// staging its input patch in shared memory.  All reductions are two-pass (per-block partials, then
+// a fixed-order sum) so results are deterministic.
+#include "common.cuh"
+#include "sgemm.cuh"
+
+#include <algorithm>
+
+namespace rn {
+
+constexpr int kC = RN_CONV_CH;          // 24 channels everywhere except the RGB input
+constexpr int kTile = 16;               // output tile edge per block
+constexpr int kPatch = 2 * kTile + 1;   // input patch edge (stride 2, 3x3, pad 1)
+constexpr int kChunk = 8;               // input channels staged per pass
+
+struct Affine {                         // per-layer block in `saved`: mean, rstd, scale, shift (24 each)
+  float v[4 * kC];
+};
+
+__device__ __forceinline__ float act_in(float y, const float* __restrict__ aff, int c) {
+  // relu(scale*y + shift) of the previous layer's BatchNorm; aff == nullptr for the RGB image
+  return aff ? fmaxf(fmaf(aff[2 * kC + c], y, aff[3 * kC + c]), 0.f) : y;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward conv: y = conv(act(in)) + bias ; optional per-block (sum, sumsq) partials
+// grid (tiles, B), block 256 (16x16 output pixels, 24 channels per thread)
+// ------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ w,
+                const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ stat_part, int hin,
+                int hout, int tiles_x) {
+  constexpr int CC = CIN < kChunk ? CIN : kChunk;
+  __shared__ float patch[CC][kPatch][kPatch];
+  __shared__ __align__(16) float wsm[CC][kC][12];
+  __shared__ float red[8][2 * kC];
+
+  const int tid = threadIdx.x, tx = tid % kTile, ty = tid / kTile;
+  const int b = blockIdx.y;
+  const int oh0 = (blockIdx.x / tiles_x) * kTile, ow0 = (blockIdx.x % tiles_x) * kTile;
+  const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
+  const float* inb = in + (size_t)b * CIN * hin * hin;
+
+  float acc[kC];
+#pragma unroll
+  for (int co = 0; co < kC; ++co) acc[co] = 0.f;
+
+  for (int ci0 = 0; ci0 < CIN; ci0 += CC) {
+    __syncthreads();
+    for (int idx = tid; idx < CC * kPatch * kPatch; idx += 256) {
+      const int ci = idx / (kPatch * kPatch), rem = idx % (kPatch * kPatch);
+      const int r = rem / kPatch, c = rem % kPatch;
+      const int ih = ih0 + r, iw = iw0 + c;
+      float v = 0.f;      // zero padding applies to the post-activation tensor
+      if (ih >= 0 && ih < hin && iw >= 0 && iw < hin) v = act_in(inb[((size_t)(ci0 + ci) * hin + ih) * hin + iw], in_aff, ci0 + ci);
+      patch[ci][r][c] = v;
+    }
+    for (int idx = tid; idx < CC * kC * 9; idx += 256) {
+      const int ci = idx / (kC * 9), rem = idx % (kC * 9);
+      const int co = rem / 9, t = rem % 9;
+      wsm[ci][co][t] = w[((size_t)co * CIN + ci0 + ci) * 9 + t];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CC; ++ci) {
+      float xv[9];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) xv[kh * 3 + kw] = patch[ci][2 * ty + kh][2 * tx + kw];
+#pragma unroll
+      for (int co = 0; co < kC; ++co) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[ci][co][0]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[ci][co][4]);
+        const float w8 = wsm[ci][co][8];
+        float a = acc[co];
+        a = fmaf(xv[0], w0.x, a); a = fmaf(xv[1], w0.y, a); a = fmaf(xv[2], w0.z, a);
+        a = fmaf(xv[3], w0.w, a); a = fmaf(xv[4], w1.x, a); a = fmaf(xv[5], w1.y, a);
+        a = fmaf(xv[6], w1.z, a); a = fmaf(xv[7], w1.w, a); a = fmaf(xv[8], w8, a);
+        acc[co] = a;
+      }
+    }
+  }
+
+  const int oh = oh0 + ty, ow = ow0 + tx;
+  const bool valid = oh < hout && ow < hout;
+  float* yb = y + (size_t)b * kC * hout * hout;
+#pragma unroll
+  for (int co = 0; co < kC; ++co) {
+    acc[co] += bias[co];
+    if (valid) yb[((size_t)co * hout + oh) * hout + ow] = acc[co];
+  }
+  if (stat_part) {
+    const int lane = tid % 32, warp = tid / 32;
+#pragma unroll
+    for (int co = 0; co < kC; ++co) {
+      float s = valid ? acc[co] : 0.f, s2 = s * s;
+      for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == 0) { red[warp][co] = s; red[warp][kC + co] = s2; }
+    }
+    __syncthreads();
+    if (tid < 2 * kC) {
+      float s = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) s += red[wv][tid];
+      stat_part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * kC + tid] = s;
+    }
+  }
+}
+
+// one warp per channel: fixed-order double sum of the per-block partials -> mean/rstd/scale/shift,
+// running-stat update (momentum, unbiased variance) as nn.BatchNorm2d does in training.
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int nblk, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ aff, float eps, float momentum,
+                                   int training) {
+  const int c = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (c >= kC) return;
+  float mean, var;
+  if (training) {
+    double s = 0.0, s2 = 0.0;
+    for (int i = lane; i < nblk; i += 32) {
+      s += part[(size_t)i * 2 * kC + c];
+      s2 += part[(size_t)i * 2 * kC + kC + c];
+    }
+    for (int o = 16; o; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const double m = s / count;
+    double v = s2 / count - m * m;
+    if (v < 0) v = 0;
+    mean = (float)m;
+    var = (float)v;
+    if (lane == 0) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(v * (count / (count > 1 ? count - 1 : 1)));
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  if (lane == 0) {
+    const float rstd = rsqrtf(var + eps);
+    const float sc = gamma[c] * rstd;
+    aff[c] = mean;
+    aff[kC + c] = rstd;
+    aff[2 * kC + c] = sc;
+    aff[3 * kC + c] = beta[c] - mean * sc;
+  }
+}
+
+// objects[b, hw, 0..23] = relu(scale*y4 + shift), objects[b, hw, 24/25] = x/y coords (model.py:208-213)
+__global__ void objects_fwd_kernel(const float* __restrict__ y, const float* __restrict__ aff, float* __restrict__ obj,
+                                   int d, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int f = i % 26;
+  const long long r = i / 26;
+  const int hw = r % (d * d);
+  const long long b = r / (d * d);
+  float v;
+  if (f < kC) {
+    v = fmaxf(fmaf(aff[2 * kC + f], y[((size_t)b * kC + f) * d * d + hw], aff[3 * kC + f]), 0.f);
+  } else {
+    const int idx = (f == kC) ? hw % d : hw / d;      // channel 24 varies along W, 25 along H
+    v = d > 1 ? (-d / 2.f + idx * ((float)d / (d - 1))) : -d / 2.f;   // linspace(-d/2, d/2, d)
+  }
+  obj[i] = v;
+}
+
+// dA[b, c, hw] = dobjects[b, hw, c]
+__global__ void objects_bwd_kernel(const float* __restrict__ dobj, float* __restrict__ dA, int d, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int hw = i % (d * d);
+  const long long r = i / (d * d);
+  const int c = r % kC;
+  const long long b = r / kC;
+  dA[i] = dobj[((size_t)b * d * d + hw) * 26 + c];
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm backward.  g = dA * (scale*y+shift > 0);  partial[b][c] = (sum g, sum g*xhat)
+// grid (24, B), block 256
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ y, const float* __restrict__ dA, const float* __restrict__ aff,
+                     float* __restrict__ part, int hw) {
+  __shared__ float red[8][2];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float mean = aff[c], rstd = aff[kC + c], sc = aff[2 * kC + c], sh = aff[3 * kC + c];
+  const size_t base = ((size_t)b * kC + c) * hw;
+  float s = 0.f, sx = 0.f;
+  for (int i = threadIdx.x; i < hw; i += 256) {
+    const float yv = y[base + i];
+    const float g = fmaf(sc, yv, sh) > 0.f ? dA[base + i] : 0.f;
+    s += g;
+    sx += g * (yv - mean) * rstd;
+  }
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+  }
+  if (threadIdx.x % 32 == 0) { red[threadIdx.x / 32][0] = s; red[threadIdx.x / 32][1] = sx; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) v += red[wv][threadIdx.x];
+    part[((size_t)b * kC + c) * 2 + threadIdx.x] = v;
+  }
+}
+
+// warp per channel: dbeta, dgamma and the coefficients of dy = k0 * (g - k1 - xhat * k2)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int B, double count, const float* __restrict__ gamma,
+                                       const float* __restrict__ aff, float* __restrict__ coef, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ dbias, int training) {
+  const int c = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (c >= kC) return;
+  double s = 0.0, sx = 0.0;
+  for (int b = lane; b < B; b += 32) {
+    s += part[((size_t)b * kC + c) * 2];
+    sx += part[((size_t)b * kC + c) * 2 + 1];
+  }
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+  }
+  if (lane == 0) {
+    dbeta[c] = (float)s;
+    dgamma[c] = (float)sx;
+    const float k0 = gamma[c] * aff[kC + c];
+    coef[c] = k0;
+    coef[kC + c] = training ? (float)(s / count) : 0.f;
+    coef[2 * kC + c] = training ? (float)(sx / count) : 0.f;
+    // the conv bias feeds straight into BatchNorm: with batch statistics its gradient is exactly 0
+    dbias[c] = training ? 0.f : k0 * (float)s;
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ dA, const float* __restrict__ aff,
+                                    const float* __restrict__ coef, float* __restrict__ dy, int hw, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (i / hw) % kC;
+  const float yv = y[i];
+  const float g = fmaf(aff[2 * kC + c], yv, aff[3 * kC + c]) > 0.f ? dA[i] : 0.f;
+  const float xhat = (yv - aff[c]) * aff[kC + c];
+  dy[i] = coef[c] * (g - coef[kC + c] - xhat * coef[2 * kC + c]);
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient: per-block partial dW[24][CIN][9] over a 16x16 tile of dy
+// grid (tiles, B), block 256: 240 threads = 5 pixel partitions x 6 co-groups(4) x 8 ci
+// ------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ dy,
+                  float* __restrict__ part, int hin, int hout, int tiles_x) {
+  constexpr int CC = CIN < kChunk ? CIN : kChunk;
+  constexpr int NPART = 5;
+  extern __shared__ __align__(16) float wg_smem[];
+  float (*patch)[kPatch][kPatch] = reinterpret_cast<float (*)[kPatch][kPatch]>(wg_smem);
+  float (*dys)[kTile * kTile] = reinterpret_cast<float (*)[kTile * kTile]>(wg_smem + CC * kPatch * kPatch);
+  float (*accs)[6][CC][37] =
+      reinterpret_cast<float (*)[6][CC][37]>(wg_smem + CC * kPatch * kPatch + kC * kTile * kTile);
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int oh0 = (blockIdx.x / tiles_x) * kTile, ow0 = (blockIdx.x % tiles_x) * kTile;
+  const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
+  const float* inb = in + (size_t)b * CIN * hin * hin;
+  const float* dyb = dy + (size_t)b * kC * hout * hout;
+  float* out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kC * CIN * 9);
+
+  for (int idx = tid; idx < kC * kTile * kTile; idx += 256) {
+    const int co = idx / (kTile * kTile), p = idx % (kTile * kTile);
+    const int oh = oh0 + p / kTile, ow = ow0 + p % kTile;
+    dys[co][p] = (oh < hout && ow < hout) ? dyb[((size_t)co * hout + oh) * hout + ow] : 0.f;
+  }
+  const int pp = tid / 48, cg = (tid % 48) / 8, ci = tid % 8;
+  const bool active = pp < NPART && ci < CC;
+
+  for (int ci0 = 0; ci0 < CIN; ci0 += CC) {
+    __syncthreads();
+    for (int idx = tid; idx < CC * kPatch * kPatch; idx += 256) {
+      const int cc = idx / (kPatch * kPatch), rem = idx % (kPatch * kPatch);
+      const int r = rem / kPatch, c = rem % kPatch;
+      const int ih = ih0 + r, iw = iw0 + c;
+      float v = 0.f;
+      if (ih >= 0 && ih < hin && iw >= 0 && iw < hin) v = act_in(inb[((size_t)(ci0 + cc) * hin + ih) * hin + iw], in_aff, ci0 + cc);
+      patch[cc][r][c] = v;
+    }
+    __syncthreads();
+    if (active) {
+      float acc[4][9];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
+      for (int p = pp; p < kTile * kTile; p += NPART) {
+        const int py = p / kTile, px = p % kTile;
+        float xv[9];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) xv[kh * 3 + kw] = patch[ci][2 * py + kh][2 * px + kw];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float g = dys[cg * 4 + j][p];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(g, xv[t], acc[j][t]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) accs[pp][cg][ci][j * 9 + t] = acc[j][t];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 6 * CC * 36; idx += 256) {
+      const int g6 = idx / (CC * 36), rem = idx % (CC * 36);
+      const int cc = rem / 36, jt = rem % 36;
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < NPART; ++q) v += accs[q][g6][cc][jt];
+      const int co = g6 * 4 + jt / 9, t = jt % 9;
+      out[((size_t)co * CIN + ci0 + cc) * 9 + t] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// data gradient (layers 2..4): dA_prev[b, ci, ih, iw] = sum_{co,kh,kw} dy[b, co, oh, ow] W[co, ci, kh, kw]
+// with ih = 2*oh + kh - 1.  Block: 32x32 input pixels of one image, thread = 2x2 input quad x 8 ci.
+// grid (tiles, B, 3 ci-chunks), block 256
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dA, int hin, int hout,
+                  int tiles_x) {
+  __shared__ float dys[kC][kTile + 1][kTile + 2];
+  __shared__ __align__(16) float wsm[kC][kChunk][12];
+  const int tid = threadIdx.x, tx = tid % kTile, ty = tid / kTile;
+  const int b = blockIdx.y, ci0 = blockIdx.z * kChunk;
+  const int q0y = (blockIdx.x / tiles_x) * kTile, q0x = (blockIdx.x % tiles_x) * kTile;   // quad == output coords
+  const float* dyb = dy + (size_t)b * kC * hout * hout;
+
+  for (int idx = tid; idx < kC * (kTile + 1) * (kTile + 1); idx += 256) {
+    const int co = idx / ((kTile + 1) * (kTile + 1)), rem = idx % ((kTile + 1) * (kTile + 1));
+    const int r = rem / (kTile + 1), c = rem % (kTile + 1);
+    const int oh = q0y + r, ow = q0x + c;
+    dys[co][r][c] = (oh < hout && ow < hout) ? dyb[((size_t)co * hout + oh) * hout + ow] : 0.f;
+  }
+  for (int idx = tid; idx < kC * kChunk * 9; idx += 256) {
+    const int co = idx / (kChunk * 9), rem = idx % (kChunk * 9);
+    const int ci = rem / 9, t = rem % 9;
+    wsm[co][ci][t] = w[((size_t)co * kC + ci0 + ci) * 9 + t];
+  }
+  __syncthreads();
+
+  // quad (i, j) covers input pixels (2i, 2j), (2i, 2j+1), (2i+1, 2j), (2i+1, 2j+1)
+  float acc[kChunk][4];
+#pragma unroll
+  for (int ci = 0; ci < kChunk; ++ci)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[ci][p] = 0.f;
+#pragma unroll 1
+  for (int co = 0; co < kC; ++co) {
+    const float d00 = dys[co][ty][tx], d01 = dys[co][ty][tx + 1], d10 = dys[co][ty + 1][tx], d11 = dys[co][ty + 1][tx + 1];
+#pragma unroll
+    for (int ci = 0; ci < kChunk; ++ci) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&wsm[co][ci][0]);   // taps (0,0) (0,1) (0,2) (1,0)
+      const float4 w1 = *reinterpret_cast<const float4*>(&wsm[co][ci][4]);   // taps (1,1) (1,2) (2,0) (2,1)
+      const float w22 = wsm[co][ci][8];
+      // (even, even): kh = 1, kw = 1
+      acc[ci][0] = fmaf(d00, w1.x, acc[ci][0]);
+      // (even, odd): kh = 1; kw = 0 -> ow = j + 1, kw = 2 -> ow = j
+      acc[ci][1] = fmaf(d01, w0.w, fmaf(d00, w1.y, acc[ci][1]));
+      // (odd, even): kw = 1; kh = 0 -> oh = i + 1, kh = 2 -> oh = i
+      acc[ci][2] = fmaf(d10, w0.y, fmaf(d00, w1.w, acc[ci][2]));
+      // (odd, odd): kh, kw in {0, 2}
+      acc[ci][3] = fmaf(d11, w0.x, fmaf(d10, w0.z, fmaf(d01, w1.z, fmaf(d00, w22, acc[ci][3]))));
+    }
+  }
+  const int ih = 2 * (q0y + ty), iw = 2 * (q0x + tx);
+  if (ih < hin && iw < hin) {
+    float* o = dA + ((size_t)b * kC + ci0) * hin * hin;
+#pragma unroll
+    for (int ci = 0; ci < kChunk; ++ci) {
+      float* oc = o + (size_t)ci * hin * hin;
+      *reinterpret_cast<float2*>(&oc[(size_t)ih * hin + iw]) = make_float2(acc[ci][0], acc[ci][1]);
+      *reinterpret_cast<float2*>(&oc[(size_t)(ih + 1) * hin + iw]) = make_float2(acc[ci][2], acc[ci][3]);
+    }
+  }
+}
+
+static size_t wgrad_smem_bytes(int cc) {
+  return ((size_t)cc * kPatch * kPatch + (size_t)kC * kTile * kTile + (size_t)5 * 6 * cc * 37) * sizeof(float);
+}
+
+struct ConvPlan {
+  int h[RN_CONV_LAYERS + 1];        // h[0] = side, h[l+1] = output edge of layer l
+  size_t y_off[RN_CONV_LAYERS];     // float offsets of y_l in `saved`
+  size_t aff_off[RN_CONV_LAYERS];
+  size_t saved_floats;
+  int tiles[RN_CONV_LAYERS];        // 16x16 output tiles per image
+  size_t scratch_floats;
+};
+
+static ConvPlan make_plan(const rn_conv_cfg& c) {
+  ConvPlan p;
+  p.h[0] = c.side;
+  size_t off = 0;
+  for (int l = 0; l < RN_CONV_LAYERS; ++l) {
+    p.h[l + 1] = p.h[l] / 2;
+    p.y_off[l] = off;
+    off += round_up((size_t)c.B * kC * p.h[l + 1] * p.h[l + 1], 64);
+    const int t = cdiv(p.h[l + 1], kTile);
+    p.tiles[l] = t * t;
+  }
+  for (int l = 0; l < RN_CONV_LAYERS; ++l) {
+    p.aff_off[l] = off;
+    off += 4 * kC;
+  }
+  p.saved_floats = off;
+  // scratch: dA + dy (largest layer), BN partials, coef, wgrad partials
+  const size_t big = round_up((size_t)c.B * kC * p.h[1] * p.h[1], 64);
+  size_t wpart = 0, spart = 0;
+  for (int l = 0; l < RN_CONV_LAYERS; ++l) {
+    const size_t cin = l == 0 ? 3 : kC;
+    wpart = std::max(wpart, (size_t)c.B * p.tiles[l] * kC * cin * 9);
+    spart = std::max(spart, (size_t)c.B * p.tiles[l] * 2 * kC);
+  }
+  p.scratch_floats = 2 * big + round_up(std::max(spart, (size_t)c.B * kC * 2), 64) + 64 * 4 + round_up(wpart, 64);
+  return p;
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+static int validate_conv(const rn_conv_cfg* c) {
+  RN_CHECK_ARG(c != nullptr, "cfg is NULL");
+  RN_CHECK_ARG(c->B > 0 && c->B <= 65535, "B must be in [1, 65535] (B=%d)", c->B);
+  RN_CHECK_ARG(c->side >= 16 && c->side % 16 == 0, "side must be a positive multiple of 16 (side=%d)", c->side);
+  return RN_OK;
+}
+
+extern "C" int rn_conv_workspace(const rn_conv_cfg* cfg, size_t* saved_floats, size_t* scratch_floats) {
+  RN_TRY(validate_conv(cfg));
+  RN_CHECK_ARG(saved_floats && scratch_floats, "output pointers are NULL");
+  ConvPlan p = make_plan(*cfg);
+  *saved_floats = p.saved_floats;
+  *scratch_floats = p.scratch_floats;
+  return RN_OK;
+}
+
+extern "C" int rn_conv_fwd(const rn_conv_cfg* cfg, const float* img, const rn_conv_layer* L, float* objects,
+                           float* saved, float* scratch, void* stream) {
+  RN_TRY(validate_conv(cfg));
+  RN_CHECK_ARG(img && L && objects && saved && scratch, "NULL pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ConvPlan p = make_plan(*cfg);
+  const float* in = img;
+  const float* in_aff = nullptr;
+  for (int l = 0; l < RN_CONV_LAYERS; ++l) {
+    RN_CHECK_ARG(L[l].w && L[l].bias && L[l].gamma && L[l].beta && L[l].running_mean && L[l].running_var,
+                 "conv layer %d has a NULL parameter", l);
+    float* y = saved + p.y_off[l];
+    float* aff = saved + p.aff_off[l];
+    const int hin = p.h[l], hout = p.h[l + 1], tx = cdiv(hout, kTile);
+    dim3 grid(p.tiles[l], cfg->B);
+    float* part = cfg->training ? scratch : nullptr;
+    if (l == 0)
+      conv_fwd_kernel<3><<<grid, 256, 0, st>>>(in, in_aff, L[l].w, L[l].bias, y, part, hin, hout, tx);
+    else
+      conv_fwd_kernel<kC><<<grid, 256, 0, st>>>(in, in_aff, L[l].w, L[l].bias, y, part, hin, hout, tx);
+    RN_LAUNCH_CHECK("conv_fwd_kernel");
+    bn_finalize_kernel<<<1, 32 * kC, 0, st>>>(scratch, p.tiles[l] * cfg->B, (double)cfg->B * hout * hout, L[l].gamma,
+                                             L[l].beta, L[l].running_mean, L[l].running_var, aff, cfg->eps,
+                                             cfg->momentum, cfg->training);
+    RN_LAUNCH_CHECK("bn_finalize_kernel");
+    in = y;
+    in_aff = aff;
+  }
+  const int d = p.h[RN_CONV_LAYERS];
+  const long long total = (long long)cfg->B * d * d * 26;
+  objects_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, in_aff, objects, d, total);
+  RN_LAUNCH_CHECK("objects_fwd_kernel");
+  return RN_OK;
+}
+
+extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float* dobjects, const rn_conv_layer* L,
+                           const float* saved, const rn_conv_grads* Gr, float* scratch, void* stream) {
+  RN_TRY(validate_conv(cfg));
+  RN_CHECK_ARG(img && dobjects && L && saved && Gr && scratch, "NULL pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ConvPlan p = make_plan(*cfg);
+  const size_t big = round_up((size_t)cfg->B * kC * p.h[1] * p.h[1], 64);
+  float* dA = scratch;
+  float* dy = scratch + big;
+  float* bnpart = dy + big;
+  size_t spart = 0;
+  for (int l = 0; l < RN_CONV_LAYERS; ++l) spart = std::max(spart, (size_t)cfg->B * p.tiles[l] * 2 * kC);
+  float* coef = bnpart + round_up(std::max(spart, (size_t)cfg->B * kC * 2), 64);
+  float* wpart = coef + 64 * 4;
+
+  const int d = p.h[RN_CONV_LAYERS];
+  {
+    const long long total = (long long)cfg->B * kC * d * d;
+    objects_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(dobjects, dA, d, total);
+    RN_LAUNCH_CHECK("objects_bwd_kernel");
+  }
+  for (int l = RN_CONV_LAYERS - 1; l >= 0; --l) {
+    RN_CHECK_ARG(Gr[l].dw && Gr[l].dbias && Gr[l].dgamma && Gr[l].dbeta, "conv grads of layer %d have a NULL pointer", l);
+    const int hin = p.h[l], hout = p.h[l + 1], hw = hout * hout, tx = cdiv(hout, kTile);
+    const float* y = saved + p.y_off[l];
+    const float* aff = saved + p.aff_off[l];
+    bn_bwd_reduce_kernel<<<dim3(kC, cfg->B), 256, 0, st>>>(y, dA, aff, bnpart, hw);
+    RN_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+    bn_bwd_finalize_kernel<<<1, 32 * kC, 0, st>>>(bnpart, cfg->B, (double)cfg->B * hw, L[l].gamma, aff, coef, Gr[l].dgamma,
+                                                 Gr[l].dbeta, Gr[l].dbias, cfg->training);
+    RN_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+    const long long total = (long long)cfg->B * kC * hw;
+    bn_bwd_apply_kernel<<<cdiv(total, 256), 256, 0, st>>>(y, dA, aff, coef, dy, hw, total);
+    RN_LAUNCH_CHECK("bn_bwd_apply_kernel");
+    // weight gradient: per-block partials, then a fixed-order sum over blocks
+    const float* in = l == 0 ? img : saved + p.y_off[l - 1];
+    const float* in_aff = l == 0 ? nullptr : saved + p.aff_off[l - 1];
+    dim3 grid(p.tiles[l], cfg->B);
+    const int cin = l == 0 ? 3 : kC;
+    if (l == 0) {
+      const size_t smem = wgrad_smem_bytes(3);
+      RN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv_wgrad_kernel<3><<<grid, 256, smem, st>>>(in, in_aff, dy, wpart, hin, hout, tx);
+    } else {
+      const size_t smem = wgrad_smem_bytes(kChunk);
+      RN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv_wgrad_kernel<kC><<<grid, 256, smem, st>>>(in, in_aff, dy, wpart, hin, hout, tx);
+    }
+    RN_LAUNCH_CHECK("conv_wgrad_kernel");
+    RN_TRY(colsum(wpart, Gr[l].dw, kC * cin * 9, 1, 1, 0, 0, 1, p.tiles[l] * cfg->B, st));
+    if (l > 0) {
+      // data gradient into dA (now sized for layer l-1's output == this layer's input)
+      const int qt = cdiv(hout, kTile);
+      conv_dgrad_kernel<<<dim3(qt * qt, cfg->B, kC / kChunk), 256, 0, st>>>(dy, L[l].w, dA, hin, hout, qt);
+      RN_LAUNCH_CHECK("conv_dgrad_kernel");
+    }
+  }
+  return RN_OK;
+}

@@ -1,0 +1,277 @@
+// relation.cu -- relation layer: shared layer-0 pieces, the fp32 SIMT path and the C-ABI dispatch.
+// Math: SURVEY.md 7.4 (restating reference model.py:104-152 and its autograd backward).
+#include "relation.cuh"
+
+namespace rn {
+
+// ------------------------------------------------------------------------------------------
+// layer 0 ("pre"): U = X W0c^T, Vb = X W0a^T + beta0, Qb = q Wq^T + b_qinj
+// ------------------------------------------------------------------------------------------
+__global__ void add_rowgroup_bias_kernel(float* __restrict__ V, const float* __restrict__ bias, long long total, int G,
+                                         int rows_per_group, long long group_stride) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long r = i / G;
+  const int c = i % G;
+  V[i] += bias[(rows_per_group ? (r / rows_per_group) * group_stride : 0) + c];
+}
+
+int relation_pre(const RelShape& s, const float* x, const float* q, const float* const* g_w, const float* const* g_b,
+                 const RelPre& pre, cudaStream_t st) {
+  const int fan0 = s.fan_in(0);
+  GemmEpilogue none;
+  // U[b,c,:] = x[b,c,:] . W0[:, 0:k]^T ; V[b,a,:] = x[b,a,:] . W0[:, k:2k]^T
+  RN_TRY(sgemm(false, true, s.B * s.n, s.G, s.k, x, s.k, g_w[0], fan0, pre.U, s.G, none, st));
+  RN_TRY(sgemm(false, true, s.B * s.n, s.G, s.k, x, s.k, g_w[0] + s.k, fan0, pre.Vb, s.G, none, st));
+  // Qb[b,:] = q[b] . Wq^T + b_qinj  (the question columns of layer qinj)
+  const float* wq = g_w[s.qinj] + (s.qinj == 0 ? 2 * s.k : s.G);
+  GemmEpilogue eb;
+  eb.bias = g_b[s.qinj];
+  RN_TRY(sgemm(false, true, s.B, s.G, s.Q, q, s.Q, wq, s.fan_in(s.qinj), pre.Qb, s.G, eb, st));
+  // fold beta0 into V: per-sample Qb when the question enters at layer 0, else the plain bias b0
+  const long long total = (long long)s.B * s.n * s.G;
+  if (s.qinj == 0)
+    add_rowgroup_bias_kernel<<<cdiv(total, 256), 256, 0, st>>>(pre.Vb, pre.Qb, total, s.G, s.n, s.G);
+  else
+    add_rowgroup_bias_kernel<<<cdiv(total, 256), 256, 0, st>>>(pre.Vb, g_b[0], total, s.G, 0, 0);
+  RN_LAUNCH_CHECK("add_rowgroup_bias_kernel");
+  return RN_OK;
+}
+
+int relation_qinj_bwd(const RelShape& s, int l, const float* q, const float* const* g_w, const float* delta,
+                      float* dq, float* const* dg_w, cudaStream_t st) {
+  const int fan = s.fan_in(l);
+  const int off = (l == 0 ? 2 * s.k : s.G);
+  GemmEpilogue none;
+  // dWq[o, j] = sum_b delta[b,o] q[b,j]
+  RN_TRY(sgemm(true, false, s.G, s.Q, s.B, delta, s.G, q, s.Q, dg_w[l] + off, fan, none, st));
+  // dq[b, j] = sum_o delta[b,o] Wq[o,j]
+  RN_TRY(sgemm(false, false, s.B, s.Q, s.G, delta, s.G, g_w[l] + off, fan, dq, s.Q, none, st));
+  return RN_OK;
+}
+
+int relation_layer0_bwd(const RelShape& s, const float* x, const float* q, const float* const* g_w, const float* dU,
+                        const float* dV, float* delta, float* dx, float* dq, float* const* dg_w,
+                        float* const* dg_b, cudaStream_t st) {
+  const int fan0 = s.fan_in(0);
+  GemmEpilogue none, acc;
+  acc.beta = 1.f;
+  // delta0[b] = sum_a dV[b,a]   (== sum over all pairs of dZ1) ; db0 = sum_b delta0
+  RN_TRY(colsum(dV, delta, s.G, s.B, 1, s.n, 0, 1, s.n, st));
+  RN_TRY(colsum(delta, dg_b[0], s.G, 1, 1, 0, 0, 1, s.B, st));
+  // dW0c = dU^T X, dW0a = dV^T X  (sum over batch and objects)
+  RN_TRY(sgemm(true, false, s.G, s.k, s.B * s.n, dU, s.G, x, s.k, dg_w[0], fan0, none, st));
+  RN_TRY(sgemm(true, false, s.G, s.k, s.B * s.n, dV, s.G, x, s.k, dg_w[0] + s.k, fan0, none, st));
+  if (s.qinj == 0) RN_TRY(relation_qinj_bwd(s, 0, q, g_w, delta, dq, dg_w, st));
+  // dX = dU W0c + dV W0a
+  RN_TRY(sgemm(false, false, s.B * s.n, s.k, s.G, dU, s.G, g_w[0], fan0, dx, s.k, none, st));
+  RN_TRY(sgemm(false, false, s.B * s.n, s.k, s.G, dV, s.G, g_w[0] + s.k, fan0, dx, s.k, acc, st));
+  return RN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 SIMT path
+// ------------------------------------------------------------------------------------------
+// H1[b, a, c, :] = relu(U[b,c,:] + Vb[b,a,:])
+__global__ void pairgen_kernel(const float* __restrict__ U, const float* __restrict__ Vb, float* __restrict__ H,
+                               int n, int G4, long long total4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int g = i % G4;
+  long long r = i / G4;
+  const int c = r % n;
+  r /= n;
+  const int a = r % n;
+  const long long b = r / n;
+  const float4 u = reinterpret_cast<const float4*>(U)[(b * n + c) * G4 + g];
+  const float4 v = reinterpret_cast<const float4*>(Vb)[(b * n + a) * G4 + g];
+  float4 h;
+  h.x = fmaxf(u.x + v.x, 0.f);
+  h.y = fmaxf(u.y + v.y, 0.f);
+  h.z = fmaxf(u.z + v.z, 0.f);
+  h.w = fmaxf(u.w + v.w, 0.f);
+  reinterpret_cast<float4*>(H)[i] = h;
+}
+
+// dZ[b, p, :] = dxg[b, :] * (H[b, p, :] > 0)
+__global__ void relu_bwd_broadcast_kernel(const float* __restrict__ dxg, const float* __restrict__ H,
+                                          float* __restrict__ dZ, long long pairs, int G, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int g = i % G;
+  const long long b = i / G / pairs;
+  dZ[i] = H[i] > 0.f ? dxg[b * G + g] : 0.f;
+}
+
+struct SimtSaved {
+  RelPre pre;
+  float* H[RN_MAX_G_LAYERS];
+};
+
+static SimtSaved simt_carve_saved(const RelShape& s, void* saved, int n_h) {
+  Carver c(saved);
+  SimtSaved out;
+  out.pre.U = c.take<float>((size_t)s.B * s.n * s.G);
+  out.pre.Vb = c.take<float>((size_t)s.B * s.n * s.G);
+  out.pre.Qb = c.take<float>((size_t)s.B * s.G);
+  for (int l = 0; l < n_h; ++l) out.H[l] = c.take<float>((size_t)s.rows * s.G);
+  return out;
+}
+
+size_t simt_saved_bytes(const RelShape& s, bool training) {
+  const size_t pre = 2 * round_up((size_t)s.B * s.n * s.G * 4, 256) + round_up((size_t)s.B * s.G * 4, 256);
+  const size_t h = round_up((size_t)s.rows * s.G * 4, 256);
+  return pre + (training ? s.L : 2) * h;     // eval ping-pongs two activation buffers
+}
+
+static size_t splitk_floats(const RelShape& s) { return (size_t)8 * 148 * 128 * 128; }
+
+size_t simt_scratch_bytes(const RelShape& s, bool training) {
+  size_t b = round_up(splitk_floats(s) * 4, 256);
+  if (training) {
+    b += 2 * round_up((size_t)s.rows * s.G * 4, 256);          // dZ ping-pong
+    b += 2 * round_up((size_t)s.B * s.n * s.G * 4, 256);       // dU, dV
+    b += round_up((size_t)s.B * s.G * 4, 256);                 // delta
+  }
+  return b;
+}
+
+int simt_relation_fwd(const RelShape& s, bool training, const float* x, const float* q, const float* const* g_w,
+                      const float* const* g_b, float* xg, void* saved, void* scratch, cudaStream_t st) {
+  const int n_h = training ? s.L : 2;
+  SimtSaved sv = simt_carve_saved(s, saved, n_h);
+  RN_TRY(relation_pre(s, x, q, g_w, g_b, sv.pre, st));
+  const long long total4 = s.rows * (s.G / 4);
+  pairgen_kernel<<<cdiv(total4, 256), 256, 0, st>>>(sv.pre.U, sv.pre.Vb, sv.H[0], s.n, s.G / 4, total4);
+  RN_LAUNCH_CHECK("pairgen_kernel");
+  const float* cur = sv.H[0];
+  for (int l = 1; l < s.L; ++l) {
+    float* nxt = sv.H[training ? l : (l & 1)];
+    GemmEpilogue ep;
+    ep.relu = 1;
+    if (l == s.qinj) {
+      ep.bias = sv.pre.Qb;
+      ep.bias_group_rows = (int)s.pairs;
+      ep.bias_group_stride = s.G;
+    } else {
+      ep.bias = g_b[l];
+    }
+    RN_TRY(sgemm(false, true, (int)s.rows, s.G, s.G, cur, s.G, g_w[l], s.fan_in(l), nxt, s.G, ep, st));
+    cur = nxt;
+  }
+  RN_TRY(colsum(cur, xg, s.G, s.B, 1, s.pairs, 0, 1, (int)s.pairs, st));
+  (void)scratch;
+  return RN_OK;
+}
+
+int simt_relation_bwd(const RelShape& s, const float* dxg, const float* x, const float* q, const float* const* g_w,
+                      const void* saved, float* dx, float* dq, float* const* dg_w, float* const* dg_b, void* scratch,
+                      cudaStream_t st) {
+  SimtSaved sv = simt_carve_saved(s, const_cast<void*>(saved), s.L);
+  Carver c(scratch);
+  float* ws = c.take<float>(splitk_floats(s));
+  float* dZa = c.take<float>((size_t)s.rows * s.G);
+  float* dZb = c.take<float>((size_t)s.rows * s.G);
+  float* dU = c.take<float>((size_t)s.B * s.n * s.G);
+  float* dV = c.take<float>((size_t)s.B * s.n * s.G);
+  float* delta = c.take<float>((size_t)s.B * s.G);
+
+  const long long total = s.rows * s.G;
+  relu_bwd_broadcast_kernel<<<cdiv(total, 256), 256, 0, st>>>(dxg, sv.H[s.L - 1], dZa, s.pairs, s.G, total);
+  RN_LAUNCH_CHECK("relu_bwd_broadcast_kernel");
+  float* dZ = dZa;
+  float* dZn = dZb;
+  for (int l = s.L - 1; l >= 1; --l) {
+    const int fan = s.fan_in(l);
+    // delta[b] = sum_pairs dZ ; db_l = sum_b delta
+    RN_TRY(colsum(dZ, delta, s.G, s.B, 1, s.pairs, 0, 1, (int)s.pairs, st));
+    RN_TRY(colsum(delta, dg_b[l], s.G, 1, 1, 0, 0, 1, s.B, st));
+    // dWh_l = dZ^T H_{l-1}
+    GemmEpilogue none;
+    RN_TRY(sgemm(true, false, s.G, s.G, (int)s.rows, dZ, s.G, sv.H[l - 1], s.G, dg_w[l], fan, none, st, ws,
+                 splitk_floats(s)));
+    if (l == s.qinj) RN_TRY(relation_qinj_bwd(s, l, q, g_w, delta, dq, dg_w, st));
+    // dZ_{l} = (dZ Wh_l) .* (H_{l-1} > 0)
+    GemmEpilogue ep;
+    ep.mask = sv.H[l - 1];
+    ep.ldmask = s.G;
+    RN_TRY(sgemm(false, false, (int)s.rows, s.G, s.G, dZ, s.G, g_w[l], fan, dZn, s.G, ep, st));
+    float* t = dZ; dZ = dZn; dZn = t;
+  }
+  // dZ is dZ1 [B, a, c, G]: dU[b,c] = sum_a, dV[b,a] = sum_c
+  RN_TRY(colsum(dZ, dU, s.G, s.B, s.n, s.pairs, 1, s.n, s.n, st));
+  RN_TRY(colsum(dZ, dV, s.G, s.B * s.n, 1, s.n, 0, 1, s.n, st));
+  RN_TRY(relation_layer0_bwd(s, x, q, g_w, dU, dV, delta, dx, dq, dg_w, dg_b, st));
+  return RN_OK;
+}
+
+}  // namespace rn
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+using namespace rn;
+
+static int validate_cfg(const rn_relation_cfg* cfg) {
+  RN_CHECK_ARG(cfg != nullptr, "cfg is NULL");
+  RN_CHECK_ARG(cfg->B > 0 && cfg->n > 0 && cfg->k > 0 && cfg->Q > 0, "B, n, k, Q must be positive (B=%d n=%d k=%d Q=%d)",
+               cfg->B, cfg->n, cfg->k, cfg->Q);
+  RN_CHECK_ARG(cfg->G > 0 && cfg->G % 4 == 0, "G must be a positive multiple of 4 (G=%d)", cfg->G);
+  RN_CHECK_ARG(cfg->L >= 2 && cfg->L <= RN_MAX_G_LAYERS, "L must be in [2,%d] (L=%d)", RN_MAX_G_LAYERS, cfg->L);
+  RN_CHECK_ARG(cfg->qinj >= 0 && cfg->qinj < cfg->L, "qinj must be in [0,L) (qinj=%d)", cfg->qinj);
+  RN_CHECK_ARG(cfg->precision >= RN_PRECISION_FP32 && cfg->precision <= RN_PRECISION_FAST, "unknown precision %d",
+               cfg->precision);
+  RN_CHECK_ARG((long long)cfg->B * cfg->n * cfg->n < (1LL << 31), "B*n*n must fit in int32");
+  return RN_OK;
+}
+
+extern "C" int rn_relation_tc_supported(const rn_relation_cfg* cfg) {
+  if (validate_cfg(cfg) != RN_OK) return 0;
+  return tc_supported(RelShape(*cfg)) ? 1 : 0;
+}
+
+extern "C" int rn_relation_workspace(const rn_relation_cfg* cfg, size_t* saved_bytes, size_t* scratch_bytes) {
+  RN_TRY(validate_cfg(cfg));
+  RN_CHECK_ARG(saved_bytes && scratch_bytes, "output pointers are NULL");
+  RelShape s(*cfg);
+  if (cfg->precision == RN_PRECISION_FP32) {
+    *saved_bytes = simt_saved_bytes(s, cfg->training != 0);
+    *scratch_bytes = simt_scratch_bytes(s, cfg->training != 0);
+  } else {
+    if (!tc_supported(s))
+      return fail(RN_ERR_UNSUPPORTED, "tcgen05 path needs G==256, L==4, n*n %% 128 == 0 (G=%d L=%d n=%d)", s.G, s.L, s.n);
+    *saved_bytes = tc_saved_bytes(s, cfg->training != 0);
+    *scratch_bytes = tc_scratch_bytes(s, cfg->training != 0);
+  }
+  return RN_OK;
+}
+
+extern "C" int rn_relation_fwd(const rn_relation_cfg* cfg, const float* x, const float* q, const float* const* h_g_w,
+                               const float* const* h_g_b, float* xg, void* saved, void* scratch, void* stream) {
+  RN_TRY(validate_cfg(cfg));
+  RN_CHECK_ARG(x && q && h_g_w && h_g_b && xg && saved && scratch, "NULL pointer argument");
+  RN_CHECK_ARG(aligned16(x) && aligned16(q) && aligned16(xg) && aligned16(saved) && aligned16(scratch),
+               "buffers must be 16-byte aligned");
+  for (int l = 0; l < cfg->L; ++l) RN_CHECK_ARG(h_g_w[l] && h_g_b[l], "g layer %d pointer is NULL", l);
+  RelShape s(*cfg);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cfg->precision == RN_PRECISION_FP32)
+    return simt_relation_fwd(s, cfg->training != 0, x, q, h_g_w, h_g_b, xg, saved, scratch, st);
+  if (!tc_supported(s)) return fail(RN_ERR_UNSUPPORTED, "tcgen05 path does not support this shape");
+  return tc_relation_fwd(s, cfg->precision, cfg->training != 0, x, q, h_g_w, h_g_b, xg, saved, scratch, st);
+}
+
+extern "C" int rn_relation_bwd(const rn_relation_cfg* cfg, const float* dxg, const float* x, const float* q,
+                               const float* const* h_g_w, const void* saved, float* dx, float* dq,
+                               float* const* h_dg_w, float* const* h_dg_b, void* scratch, void* stream) {
+  RN_TRY(validate_cfg(cfg));
+  RN_CHECK_ARG(cfg->training != 0, "rn_relation_bwd needs a cfg with training=1 (same as the forward call)");
+  RN_CHECK_ARG(dxg && x && q && h_g_w && saved && dx && dq && h_dg_w && h_dg_b && scratch, "NULL pointer argument");
+  for (int l = 0; l < cfg->L; ++l) RN_CHECK_ARG(h_g_w[l] && h_dg_w[l] && h_dg_b[l], "g layer %d pointer is NULL", l);
+  RelShape s(*cfg);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cfg->precision == RN_PRECISION_FP32)
+    return simt_relation_bwd(s, dxg, x, q, h_g_w, saved, dx, dq, h_dg_w, h_dg_b, scratch, st);
+  if (!tc_supported(s)) return fail(RN_ERR_UNSUPPORTED, "tcgen05 path does not support this shape");
+  return tc_relation_bwd(s, cfg->precision, dxg, x, q, h_g_w, saved, dx, dq, h_dg_w, h_dg_b, scratch, st);
+}

@@ -1,0 +1,220 @@
+// sgemm.cuh -- generic fp32 SIMT GEMM with fused epilogues.
+//
+// Used by the RN_PRECISION_FP32 relation path (any shape), the f-MLP head and the small layer-0
+// products of the tcgen05 path.  C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] (+ epilogue).
+// 128x128x16 tiles, 256 threads, 8x8 micro-tiles, register-prefetched smem staging; arbitrary
+// leading dimensions and sub-matrix offsets (scalar, bounds-checked global loads), optional
+// split-K with a deterministic second-pass reduction.
+#pragma once
+
+#include "common.cuh"
+
+namespace rn {
+
+struct GemmEpilogue {
+  const float* bias = nullptr;   // per-column bias [N]; row r uses bias + (r / bias_group_rows) * bias_group_stride
+  int bias_group_rows = 0;       // 0: one bias vector for all rows
+  long long bias_group_stride = 0;
+  int relu = 0;                  // max(v, 0)
+  const float* mask = nullptr;   // multiply by (mask[r*ldmask + c] > 0)
+  long long ldmask = 0;
+  float alpha = 1.f;
+  float beta = 0.f;              // C = v + beta * C_old
+};
+
+constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 16, kGemmThreads = 256;
+
+template <bool AT, bool BT>
+__global__ void __launch_bounds__(kGemmThreads)
+sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long long lda, const float* __restrict__ B,
+             long long ldb, float* __restrict__ C, long long ldc, GemmEpilogue ep, int k_chunk,
+             long long split_stride) {
+  __shared__ __align__(16) float As[kGemmBK][kGemmBM + 4];
+  __shared__ __align__(16) float Bs[kGemmBK][kGemmBN + 4];
+
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * kGemmBN;
+  const int k_begin = blockIdx.z * k_chunk;
+  const int k_end = min(K, k_begin + k_chunk);
+  const int tx = tid % 16, ty = tid / 16;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float ra[8], rb[8];
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m, k;
+      if (AT) { m = tid % 128; k = tid / 128 + 2 * i; }      // memory contiguous along m
+      else    { k = tid % 16;  m = tid / 16 + 16 * i; }      // memory contiguous along k
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < k_end) v = AT ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int n, k;
+      if (BT) { k = tid % 16;  n = tid / 16 + 16 * i; }      // B[n*ldb + k]
+      else    { n = tid % 128; k = tid / 128 + 2 * i; }      // B[k*ldb + n]
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < k_end) v = BT ? B[(long long)gn * ldb + gk] : B[(long long)gk * ldb + gn];
+      rb[i] = v;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m, k;
+      if (AT) { m = tid % 128; k = tid / 128 + 2 * i; }
+      else    { k = tid % 16;  m = tid / 16 + 16 * i; }
+      As[k][m] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int n, k;
+      if (BT) { k = tid % 16;  n = tid / 16 + 16 * i; }
+      else    { n = tid % 128; k = tid / 128 + 2 * i; }
+      Bs[k][n] = rb[i];
+    }
+  };
+
+  if (k_begin < k_end) {
+    load_tiles(k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += kGemmBK) {
+      store_tiles();
+      __syncthreads();
+      if (k0 + kGemmBK < k_end) load_tiles(k0 + kGemmBK);
+#pragma unroll
+      for (int kk = 0; kk < kGemmBK; ++kk) {
+        float a[8], b[8];
+        *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+        *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  float* Cz = C + (long long)blockIdx.z * split_stride;
+  const bool raw = split_stride != 0;   // split-K partials: no epilogue here
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= M) continue;
+    const float* bias_row = nullptr;
+    if (!raw && ep.bias)
+      bias_row = ep.bias + (ep.bias_group_rows ? (long long)(gm / ep.bias_group_rows) * ep.bias_group_stride : 0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (!raw) {
+        v *= ep.alpha;
+        if (bias_row) v += bias_row[gn];
+        if (ep.relu) v = fmaxf(v, 0.f);
+        if (ep.mask) v = ep.mask[(long long)gm * ep.ldmask + gn] > 0.f ? v : 0.f;
+        if (ep.beta != 0.f) v += ep.beta * Cz[(long long)gm * ldc + gn];
+      }
+      Cz[(long long)gm * ldc + gn] = v;
+    }
+  }
+}
+
+// second pass of split-K: C = epilogue(sum_z partial[z])
+static __global__ void splitk_reduce_kernel(int M, int N, int splits, const float* __restrict__ part, float* __restrict__ C,
+                                     long long ldc, GemmEpilogue ep) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * N) return;
+  const int gm = idx / N, gn = idx % N;
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += part[(long long)z * M * N + idx];
+  v *= ep.alpha;
+  if (ep.bias) v += ep.bias[(ep.bias_group_rows ? (long long)(gm / ep.bias_group_rows) * ep.bias_group_stride : 0) + gn];
+  if (ep.relu) v = fmaxf(v, 0.f);
+  if (ep.mask) v = ep.mask[(long long)gm * ep.ldmask + gn] > 0.f ? v : 0.f;
+  if (ep.beta != 0.f) v += ep.beta * C[(long long)gm * ldc + gn];
+  C[(long long)gm * ldc + gn] = v;
+}
+
+// Launch.  `splitk_ws` (floats, >= splits*M*N) enables split-K when K is long and the tile grid small.
+inline int sgemm(bool at, bool bt, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
+                 float* C, long long ldc, const GemmEpilogue& ep, cudaStream_t st, float* splitk_ws = nullptr,
+                 size_t splitk_ws_floats = 0) {
+  if (M <= 0 || N <= 0) return RN_OK;
+  dim3 grid(cdiv(M, kGemmBM), cdiv(N, kGemmBN), 1);
+  int splits = 1;
+  const long long tiles = (long long)grid.x * grid.y;
+  if (splitk_ws && K >= 4096 && tiles < 2LL * sm_count()) {
+    splits = (int)min((long long)cdiv(K, 1024), max(1LL, (4LL * sm_count()) / tiles));
+    while (splits > 1 && (size_t)splits * M * N > splitk_ws_floats) --splits;
+  }
+  int k_chunk = K;
+  long long split_stride = 0;
+  float* out = C;
+  long long ld_out = ldc;
+  if (splits > 1) {
+    k_chunk = cdiv(cdiv(K, splits), kGemmBK) * kGemmBK;
+    splits = cdiv(K, k_chunk);
+    grid.z = splits;
+    split_stride = (long long)M * N;
+    out = splitk_ws;
+    ld_out = N;
+  }
+  if (at && bt) sgemm_kernel<true, true><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+  else if (at) sgemm_kernel<true, false><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+  else if (bt) sgemm_kernel<false, true><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+  else sgemm_kernel<false, false><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+  RN_LAUNCH_CHECK("sgemm_kernel");
+  if (splits > 1) {
+    const long long total = (long long)M * N;
+    splitk_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(M, N, splits, splitk_ws, C, ldc, ep);
+    RN_LAUNCH_CHECK("splitk_reduce_kernel");
+  }
+  return RN_OK;
+}
+
+// ---- strided column sums -----------------------------------------------------------------
+// out[(g1*n2 + g2), :] = sum_{i<count} A[(g1*s1 + g2*s2 + i*si), :]   (rows of width N, ld = N)
+static __global__ void colsum_kernel(const float* __restrict__ A, float* __restrict__ out, int N, int n2, long long s1,
+                              long long s2, long long si, int count) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.y * 32 + threadIdx.x;
+  const int g = blockIdx.x;
+  const int g1 = g / n2, g2 = g % n2;
+  const float* base = A + (g1 * s1 + g2 * s2) * N;
+  float acc = 0.f;
+  if (col < N)
+    for (int i = threadIdx.y; i < count; i += 8) acc += base[i * si * N + col];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float v = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) v += red[y][threadIdx.x];
+    out[(long long)g * N + col] = v;
+  }
+}
+
+inline int colsum(const float* A, float* out, int N, int n1, int n2, long long s1, long long s2, long long si,
+                  int count, cudaStream_t st) {
+  if (n1 * n2 <= 0) return RN_OK;
+  dim3 grid(n1 * n2, cdiv(N, 32)), block(32, 8);
+  colsum_kernel<<<grid, block, 0, st>>>(A, out, N, n2, s1, s2, si, count);
+  RN_LAUNCH_CHECK("colsum_kernel");
+  return RN_OK;
+}
+
+}  // namespace rn

@@ -1,0 +1,268 @@
+"""torch.autograd bindings of the C-ABI entry points (one Function per reference span).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; all arithmetic of
+these ops happens in librn_b200.so.  Every op requires CUDA tensors and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import PRECISION, AdamCfg, ConvCfg, ConvGrads, ConvLayer, FCfg, RelationCfg, check, lib, ptr_array
+
+_scratch: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def _scratch_bytes(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
+    """Grow-only per-device scratch (dead between calls; all use is ordered on the current stream)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+# ---- optional CUDA-event timers around the relation launches (bench.py's roofline leg) ----------
+_timers_on = False
+_timer_events: Dict[str, list] = {}
+
+
+def timers_enable(flag: bool) -> None:
+    global _timers_on
+    _timers_on = bool(flag)
+    if flag:
+        _timer_events.clear()
+
+
+class _Timed:
+    """Records a CUDA event pair on the current stream around a C-ABI call when timers are enabled."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _timers_on:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timers_on:
+            self.e1.record()
+            _timer_events.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
+
+def timers_collect() -> Dict[str, list]:
+    """Milliseconds per recorded call (synchronises)."""
+    torch.cuda.synchronize()
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in _timer_events.items()}
+
+
+def _require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("relationnetworks_clevr_b200 ops run on CUDA (sm_100a) tensors only; "
+                               "there is no CPU path (use oracle/ for CPU checks in tests)")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def relation_cfg(B, n, k, Q, G, L, qinj, precision: str, training: bool) -> RelationCfg:
+    return RelationCfg(B, n, k, Q, G, L, qinj, PRECISION[precision], int(training))
+
+
+def tc_supported(n: int, G: int, L: int, k: int = 26, Q: int = 128, qinj: int = 0) -> bool:
+    cfg = relation_cfg(1, n, k, Q, G, L, qinj, "parity", False)
+    return bool(lib().rn_relation_tc_supported(C.byref(cfg)))
+
+
+class RelationFunction(torch.autograd.Function):
+    """x_g = sum over all n*n ordered pairs of g([x_c | x_a | q])  (reference model.py:104-152).
+
+    forward(x [B,n,k], q [B,Q], qinj, precision, w0, b0, ..., w_{L-1}, b_{L-1}) -> x_g [B,G]
+    """
+
+    @staticmethod
+    def forward(ctx, x, q, qinj, precision, *wb):
+        _require_cuda(x, q, *wb)
+        L = len(wb) // 2
+        ws = [_f32c(t) for t in wb[0::2]]
+        bs = [_f32c(t) for t in wb[1::2]]
+        x_, q_ = _f32c(x), _f32c(q)
+        B, n, k = x_.shape
+        Q, G = q_.shape[1], ws[0].shape[0]
+        training = any(ctx.needs_input_grad)      # forward runs with grad mode off; this is the autograd signal
+        cfg = relation_cfg(B, n, k, Q, G, L, qinj, precision, training)
+        for l, w in enumerate(ws):
+            fan = (2 * k if l == 0 else G) + (Q if l == qinj else 0)
+            if tuple(w.shape) != (G, fan):
+                raise RuntimeError(f"g layer {l} weight has shape {tuple(w.shape)}, expected {(G, fan)}")
+        sb, cb = C.c_size_t(), C.c_size_t()
+        check(lib().rn_relation_workspace(C.byref(cfg), C.byref(sb), C.byref(cb)), "rn_relation_workspace")
+        saved = torch.empty(max(sb.value, 256), dtype=torch.uint8, device=x.device)
+        scratch = _scratch_bytes(x.device, "relation", cb.value)
+        xg = torch.empty(B, G, dtype=torch.float32, device=x.device)
+        with _Timed("relation_fwd"):
+            check(lib().rn_relation_fwd(C.byref(cfg), x_.data_ptr(), q_.data_ptr(), ptr_array(ws), ptr_array(bs),
+                                        xg.data_ptr(), saved.data_ptr(), scratch.data_ptr(), _stream()),
+                  "rn_relation_fwd")
+        if training:
+            ctx.cfg = cfg
+            ctx.saved_buf = saved
+            ctx.L = L
+            ctx.save_for_backward(x_, q_, *ws)
+        return xg
+
+    @staticmethod
+    def backward(ctx, dxg):
+        x_, q_, *ws = ctx.saved_tensors
+        cfg, L = ctx.cfg, ctx.L
+        dxg_ = _f32c(dxg)
+        dx = torch.empty_like(x_)
+        dq = torch.empty_like(q_)
+        dws = [torch.empty_like(w) for w in ws]
+        dbs = [torch.empty(w.shape[0], dtype=torch.float32, device=x_.device) for w in ws]
+        sb, cb = C.c_size_t(), C.c_size_t()
+        check(lib().rn_relation_workspace(C.byref(cfg), C.byref(sb), C.byref(cb)), "rn_relation_workspace")
+        scratch = _scratch_bytes(x_.device, "relation", cb.value)
+        with _Timed("relation_bwd"):
+            check(lib().rn_relation_bwd(C.byref(cfg), dxg_.data_ptr(), x_.data_ptr(), q_.data_ptr(), ptr_array(ws),
+                                        ctx.saved_buf.data_ptr(), dx.data_ptr(), dq.data_ptr(), ptr_array(dws),
+                                        ptr_array(dbs), scratch.data_ptr(), _stream()), "rn_relation_bwd")
+        ctx.saved_buf = None
+        grads = []
+        for dw, db in zip(dws, dbs):
+            grads += [dw, db]
+        return (dx, dq, None, None, *grads)
+
+
+class FHeadFunction(torch.autograd.Function):
+    """log_softmax(fc3(relu(dropout(fc2(relu(fc1(x_g)))))))  (reference model.py:155-162).
+
+    ``drop_mask`` is a uint8 [B,F2] keep-mask drawn by the caller from torch's RNG (or None)."""
+
+    @staticmethod
+    def forward(ctx, xg, w1, b1, w2, b2, w3, b3, drop_mask, keep_scale):
+        _require_cuda(xg, w1, b1, w2, b2, w3, b3, drop_mask)
+        t = [_f32c(v) for v in (xg, w1, b1, w2, b2, w3, b3)]
+        B, G = t[0].shape
+        F1, F2, A = t[1].shape[0], t[3].shape[0], t[5].shape[0]
+        cfg = FCfg(B, G, F1, F2, A, float(keep_scale))
+        logp = torch.empty(B, A, dtype=torch.float32, device=xg.device)
+        saved = torch.empty(B * (F1 + F2), dtype=torch.float32, device=xg.device)
+        mask_ptr = drop_mask.data_ptr() if drop_mask is not None else None
+        if drop_mask is not None and (drop_mask.dtype != torch.uint8 or tuple(drop_mask.shape) != (B, F2)):
+            raise RuntimeError("drop_mask must be uint8 [B, F2]")
+        check(lib().rn_f_fwd(C.byref(cfg), *[v.data_ptr() for v in t], mask_ptr, logp.data_ptr(), saved.data_ptr(),
+                             _stream()), "rn_f_fwd")
+        ctx.cfg = cfg
+        ctx.has_mask = drop_mask is not None
+        ctx.save_for_backward(logp, saved, t[0], t[1], t[3], t[5], drop_mask if drop_mask is not None else logp)
+        return logp
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        logp, saved, xg, w1, w2, w3, mask = ctx.saved_tensors
+        cfg = ctx.cfg
+        dev = xg.device
+        dl = _f32c(dlogp)
+        dxg = torch.empty_like(xg)
+        dw1, dw2, dw3 = torch.empty_like(w1), torch.empty_like(w2), torch.empty_like(w3)
+        db1 = torch.empty(cfg.F1, dtype=torch.float32, device=dev)
+        db2 = torch.empty(cfg.F2, dtype=torch.float32, device=dev)
+        db3 = torch.empty(cfg.A, dtype=torch.float32, device=dev)
+        scratch = torch.empty(cfg.B * (cfg.A + cfg.F2 + cfg.F1), dtype=torch.float32, device=dev)
+        check(lib().rn_f_bwd(C.byref(cfg), dl.data_ptr(), logp.data_ptr(), xg.data_ptr(), w1.data_ptr(), w2.data_ptr(),
+                             w3.data_ptr(), mask.data_ptr() if ctx.has_mask else None, saved.data_ptr(),
+                             dxg.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(),
+                             dw3.data_ptr(), db3.data_ptr(), scratch.data_ptr(), _stream()), "rn_f_bwd")
+        return dxg, dw1, db1, dw2, db2, dw3, db3, None, None
+
+
+def _conv_layers(params, running) -> C.Array:
+    arr = (ConvLayer * 4)()
+    for l in range(4):
+        w, b, g, beta = params[4 * l: 4 * l + 4]
+        rm, rv = running[2 * l: 2 * l + 2]
+        arr[l] = ConvLayer(w.data_ptr(), b.data_ptr(), g.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr())
+    return arr
+
+
+class ConvObjectsFunction(torch.autograd.Function):
+    """objects [B, d*d, 26] = coords-augmented output of 4 x [conv3x3 s2 p1 -> BatchNorm -> ReLU]
+    (reference model.py:22-36 and 192-201).
+
+    forward(img, training, eps, momentum, running(8 tensors, updated in place), 16 params)
+    params per layer: conv weight, conv bias, bn weight, bn bias."""
+
+    @staticmethod
+    def forward(ctx, img, training, eps, momentum, running, *params):
+        _require_cuda(img, *params, *running)
+        img_ = _f32c(img)
+        ps = [_f32c(p) for p in params]
+        for r in running:
+            if r.dtype != torch.float32 or not r.is_contiguous():
+                raise RuntimeError("BatchNorm running statistics must be contiguous fp32")
+        B, cin, side, side2 = img_.shape
+        if cin != 3 or side != side2:
+            raise RuntimeError(f"expected [B,3,S,S] images, got {tuple(img_.shape)}")
+        cfg = ConvCfg(B, side, int(training), float(eps), float(momentum))
+        sf, cf = C.c_size_t(), C.c_size_t()
+        check(lib().rn_conv_workspace(C.byref(cfg), C.byref(sf), C.byref(cf)), "rn_conv_workspace")
+        saved = torch.empty(sf.value, dtype=torch.float32, device=img.device)
+        scratch = _scratch_bytes(img.device, "conv", cf.value * 4)
+        d = side // 16
+        objects = torch.empty(B, d * d, 26, dtype=torch.float32, device=img.device)
+        layers = _conv_layers(ps, running)
+        check(lib().rn_conv_fwd(C.byref(cfg), img_.data_ptr(), layers, objects.data_ptr(), saved.data_ptr(),
+                                scratch.data_ptr(), _stream()), "rn_conv_fwd")
+        if any(ctx.needs_input_grad):
+            ctx.cfg = cfg
+            ctx.saved_buf = saved
+            ctx.running = running
+            ctx.scratch_floats = cf.value
+            ctx.save_for_backward(img_, *ps)
+        return objects
+
+    @staticmethod
+    def backward(ctx, dobjects):
+        img_, *ps = ctx.saved_tensors
+        cfg = ctx.cfg
+        dobj = _f32c(dobjects)
+        grads = [torch.empty_like(p) for p in ps]
+        garr = (ConvGrads * 4)()
+        for l in range(4):
+            garr[l] = ConvGrads(*[g.data_ptr() for g in grads[4 * l: 4 * l + 4]])
+        layers = _conv_layers(ps, ctx.running)
+        scratch = _scratch_bytes(img_.device, "conv", ctx.scratch_floats * 4)
+        check(lib().rn_conv_bwd(C.byref(cfg), img_.data_ptr(), dobj.data_ptr(), layers, ctx.saved_buf.data_ptr(), garr,
+                                scratch.data_ptr(), _stream()), "rn_conv_bwd")
+        ctx.saved_buf = None
+        return (None, None, None, None, None, *grads)
+
+
+def clip_adam_(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+               lr: float, clip_norm: float = 50.0, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+               grad_scale: float = 1.0) -> torch.Tensor:
+    """Fused clip_grad_norm + Adam(weight_decay) on flat fp32 buffers (reference train.py:45-48, 330).
+    Returns the (pre-clip) total gradient norm as a 1-element device tensor."""
+    _require_cuda(params, grads, exp_avg, exp_avg_sq)
+    n = params.numel()
+    cfg = AdamCfg(n, lr, betas[0], betas[1], eps, weight_decay, clip_norm if clip_norm else 0.0, grad_scale, step)
+    norm_scratch = _scratch_bytes(params.device, "adam", 4 * 1032)
+    total = torch.empty(1, dtype=torch.float32, device=params.device)
+    check(lib().rn_clip_adam(C.byref(cfg), params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(),
+                             exp_avg_sq.data_ptr(), norm_scratch.data_ptr(), total.data_ptr(), _stream()), "rn_clip_adam")
+    return total

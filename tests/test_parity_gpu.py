@@ -1,0 +1,234 @@
+"""GPU parity: every C-ABI entry point against the CPU oracle on identical inputs, and the whole
+model against the golden fixtures produced by the unmodified reference.
+
+Tolerance metric everywhere: max|got - ref| / max|ref|.
+  fp32 (SIMT) kernels: 2e-4 (summation order only)
+  parity tcgen05 kernels: 1e-3 (BASELINE.json north_star: "within 1e-3 fp32 relative tolerance")
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import relationnetworks_clevr_b200 as R
+from oracle import rn_oracle as O
+from relationnetworks_clevr_b200 import ops
+from tests.golden_util import CASES, case_inputs, case_params, golden_grad_check, load_npz
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 2e-4
+TOL_PARITY = 1e-3
+DEV = "cuda"
+
+SHAPES = {
+    # name: (B, n, k, Q, G, qinj)
+    "fp_d4": (3, 16, 26, 128, 256, 0),
+    "fp_d8": (2, 64, 26, 128, 256, 0),
+    "ir_d8": (2, 64, 26, 128, 256, 2),
+    "sd": (5, 12, 7, 256, 512, 0),
+    "ir_sd": (3, 12, 7, 256, 512, 2),
+    "odd": (2, 9, 5, 24, 64, 1),
+}
+
+
+def _g_params(n, k, Q, G, qinj, gen, scale=1.0):
+    out = []
+    for l in range(4):
+        fan = (2 * k if l == 0 else G) + (Q if l == qinj else 0)
+        w = (torch.rand(G, fan, generator=gen) * 2 - 1) * scale / fan ** 0.5
+        b = (torch.rand(G, generator=gen) * 2 - 1) * 0.1
+        out.append((w, b))
+    return out
+
+
+def _relation_case(name, precision, tol):
+    B, n, k, Q, G, qinj = SHAPES[name]
+    gen = torch.Generator().manual_seed(hash(name) % 1000)
+    x = torch.randn(B, n, k, generator=gen)
+    q = torch.randn(B, Q, generator=gen)
+    gp = _g_params(n, k, Q, G, qinj, gen, scale=2.0)
+    dxg = torch.randn(B, G, generator=gen)
+    # oracle (fp64 for a clean yardstick)
+    x64, q64 = x.double().requires_grad_(True), q.double().requires_grad_(True)
+    gp64 = [(w.double().requires_grad_(True), b.double().requires_grad_(True)) for w, b in gp]
+    xg_ref = O.g_mlp_dense(x64, q64, gp64, qinj)
+    xg_ref.backward(dxg.double())
+    # CUDA
+    xc, qc = x.to(DEV).requires_grad_(True), q.to(DEV).requires_grad_(True)
+    wb = []
+    for w, b in gp:
+        wb += [w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)]
+    xg = ops.RelationFunction.apply(xc, qc, qinj, precision, *wb)
+    xg.backward(dxg.to(DEV))
+    errs = {"xg": O.rel_err(xg.detach().cpu(), xg_ref.detach())}
+    errs["dx"] = O.rel_err(xc.grad.cpu(), x64.grad)
+    errs["dq"] = O.rel_err(qc.grad.cpu(), q64.grad)
+    for l in range(4):
+        errs[f"dW{l}"] = O.rel_err(wb[2 * l].grad.cpu(), gp64[l][0].grad)
+        errs[f"db{l}"] = O.rel_err(wb[2 * l + 1].grad.cpu(), gp64[l][1].grad)
+    bad = {k_: v for k_, v in errs.items() if not v <= tol}
+    assert not bad, (name, precision, bad)
+    return errs
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_relation_fp32_matches_oracle(name):
+    _relation_case(name, "fp32", TOL_FP32)
+
+
+@pytest.mark.parametrize("name", ["fp_d4", "fp_d8", "ir_d8"])
+@pytest.mark.parametrize("precision", ["parity"])
+def test_relation_tcgen05_matches_oracle(name, precision):
+    B, n, k, Q, G, qinj = SHAPES[name]
+    if not ops.tc_supported(n, G, 4, k, Q, qinj):
+        pytest.skip("tcgen05 path does not support this shape")
+    _relation_case(name, precision, TOL_PARITY)
+
+
+def test_relation_eval_forward_and_determinism():
+    B, n, k, Q, G, qinj = SHAPES["fp_d8"]
+    gen = torch.Generator().manual_seed(5)
+    x, q = torch.randn(B, n, k, generator=gen).to(DEV), torch.randn(B, Q, generator=gen).to(DEV)
+    wb = []
+    for w, b in _g_params(n, k, Q, G, qinj, gen):
+        wb += [w.to(DEV), b.to(DEV)]
+    for precision in ("fp32", "parity"):
+        if precision != "fp32" and not ops.tc_supported(n, G, 4, k, Q, qinj):
+            continue
+        with torch.no_grad():
+            a = ops.RelationFunction.apply(x, q, qinj, precision, *wb)
+            b_ = ops.RelationFunction.apply(x, q, qinj, precision, *wb)
+        assert torch.equal(a, b_), precision          # no atomics in the pair-sum: bitwise reproducible
+        ref = O.g_mlp_dense(x.cpu().double(), q.cpu().double(), [(wb[2 * l].cpu().double(), wb[2 * l + 1].cpu().double()) for l in range(4)], qinj)
+        assert O.rel_err(a.cpu(), ref) < (TOL_FP32 if precision == "fp32" else TOL_PARITY)
+
+
+@pytest.mark.parametrize("dims", [(7, 256, 256, 256, 28), (5, 512, 512, 1024, 28)])
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_f_head_matches_oracle(dims, use_mask):
+    B, G, F1, F2, A = dims
+    gen = torch.Generator().manual_seed(B + F2)
+    p = {"rl.f_fc1.weight": torch.randn(F1, G, generator=gen) / G ** 0.5, "rl.f_fc1.bias": torch.randn(F1, generator=gen) * 0.1,
+         "rl.f_fc2.weight": torch.randn(F2, F1, generator=gen) / F1 ** 0.5, "rl.f_fc2.bias": torch.randn(F2, generator=gen) * 0.1,
+         "rl.f_fc3.weight": torch.randn(A, F2, generator=gen) / F2 ** 0.5, "rl.f_fc3.bias": torch.randn(A, generator=gen) * 0.1}
+    xg = torch.randn(B, G, generator=gen) * 3
+    mask = (torch.rand(B, F2, generator=gen) > 0.5) if use_mask else None
+    dlogp = torch.randn(B, A, generator=gen)
+    p64 = {k_: v.double().requires_grad_(True) for k_, v in p.items()}
+    xg64 = xg.double().requires_grad_(True)
+    ref = O.f_mlp(p64, xg64, 0.5, use_mask, mask)
+    ref.backward(dlogp.double())
+    pc = {k_: v.to(DEV).requires_grad_(True) for k_, v in p.items()}
+    xgc = xg.to(DEV).requires_grad_(True)
+    got = ops.FHeadFunction.apply(xgc, pc["rl.f_fc1.weight"], pc["rl.f_fc1.bias"], pc["rl.f_fc2.weight"], pc["rl.f_fc2.bias"],
+                                  pc["rl.f_fc3.weight"], pc["rl.f_fc3.bias"],
+                                  mask.to(DEV).to(torch.uint8) if use_mask else None, 2.0)
+    got.backward(dlogp.to(DEV))
+    assert O.rel_err(got.detach().cpu(), ref.detach()) < TOL_FP32
+    assert O.rel_err(xgc.grad.cpu(), xg64.grad) < TOL_FP32
+    for k_ in p:
+        assert O.rel_err(pc[k_].grad.cpu(), p64[k_].grad) < TOL_FP32, k_
+
+
+def _conv_params(seed):
+    p = O.seeded_params(O.HYPERPARAMS["original-fp"], 82, 28, seed)
+    return {k_: v for k_, v in p.items() if k_.startswith("conv.")}
+
+
+@pytest.mark.parametrize("B,side", [(3, 32), (2, 64), (2, 128), (1, 192)])
+@pytest.mark.parametrize("training", [True, False])
+def test_conv_objects_match_oracle(B, side, training):
+    p = _conv_params(side + B)
+    img = O.uniform_images(B, side, seed=side)
+    d = side // 16
+    dobj = torch.randn(B, d * d, 26, generator=torch.Generator().manual_seed(1))
+    p64 = {k_: (v.double().requires_grad_("running" not in k_)) for k_, v in p.items()}
+    running = {}
+    feat = O.conv_features(p64, img.double(), training, running)
+    obj_ref = O.objects_from_features(feat)
+    obj_ref.backward(dobj.double())
+    m = R.ConvInputModel()
+    m.load_state_dict({k_[len("conv."):]: v for k_, v in p.items()}, strict=False)
+    m.to(DEV).train(training)
+    obj = m.objects(img.to(DEV))
+    obj.backward(dobj.to(DEV))
+    assert O.rel_err(obj.detach().cpu(), obj_ref.detach()) < TOL_FP32
+    for name, prm in m.named_parameters():
+        ref = p64["conv." + name].grad
+        if name.startswith("conv") and name.endswith("bias") and training:
+            assert float(prm.grad.abs().max()) == 0.0      # exactly zero by construction (BN removes it)
+            continue
+        assert O.rel_err(prm.grad.cpu(), ref) < 5e-4, name
+    if training:
+        for i in range(1, 5):
+            for s in ("running_mean", "running_var"):
+                got = getattr(getattr(m, f"batchNorm{i}"), s).cpu()
+                assert O.rel_err(got, running[f"conv.batchNorm{i}.{s}"]) < TOL_FP32
+    # the reference-shaped [B,24,d,d] view
+    with torch.no_grad():
+        m.eval()
+        f2 = m(img.to(DEV))
+        assert f2.shape == (B, 24, d, d)
+
+
+def test_clip_adam_matches_oracle():
+    gen = torch.Generator().manual_seed(9)
+    n = 100_003
+    w, g = torch.randn(n, generator=gen), torch.randn(n, generator=gen) * 3
+    wr, m, v = w.clone(), torch.zeros(n), torch.zeros(n)
+    wc, mc, vc = w.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        total_ref = O.clip_and_adam([wr], [g.clone()], [m], [v], step, lr=1e-3)
+        total = ops.clip_adam_(wc, g.to(DEV), mc, vc, step, lr=1e-3)
+        assert abs(float(total) - float(total_ref)) < 1e-4 * float(total_ref)
+        assert torch.allclose(wc.cpu(), wr, rtol=2e-5, atol=2e-6)
+
+
+class _Args:
+    qdict_size, adict_size = 82, 28
+
+
+def _build(stem, precision):
+    hyp, p = case_params(stem)
+    m = R.RN(_Args, hyp)
+    m.load_state_dict(p, strict=False)
+    m.to(DEV)
+    m.rl.precision = precision
+    return hyp, m
+
+
+@pytest.mark.parametrize("stem", list(CASES))
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
+def test_model_eval_matches_reference_golden(stem, precision):
+    z = load_npz(stem + "_eval")
+    hyp, m = _build(stem, precision)
+    img, qst = case_inputs(z)
+    m.eval()
+    with torch.no_grad():
+        logp = m(img.to(DEV), qst.to(DEV)).cpu()
+    tol = TOL_FP32 if precision == "fp32" else TOL_PARITY
+    assert O.rel_err(logp, torch.from_numpy(z["logp"])) < tol
+    assert torch.equal(logp.argmax(1), torch.from_numpy(z["logp"]).argmax(1))
+
+
+@pytest.mark.parametrize("stem", [s for s in CASES if s != "seeded_original_fp_d12"])
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
+def test_model_train_step_matches_reference_golden(stem, precision):
+    z = load_npz(stem + "_train")
+    hyp, m = _build(stem, precision)
+    img, qst = case_inputs(z)
+    m.train()
+    m.rl.dropout_mask_override = torch.from_numpy(z["dropout_mask"]).to(torch.uint8)
+    logp = m(img.to(DEV), qst.to(DEV))
+    loss = F.nll_loss(logp, torch.from_numpy(z["label"]).to(DEV))
+    loss.backward()
+    tol = TOL_FP32 if precision == "fp32" else TOL_PARITY
+    assert O.rel_err(logp.detach().cpu(), torch.from_numpy(z["logp"])) < tol
+    assert abs(float(loss) - float(z["loss"])) < tol * max(1.0, abs(float(z["loss"])))
+    errs = {}
+    for name, prm in m.named_parameters():
+        if f"grad/{name}/l2" in z.files:
+            golden_grad_check(z, name, prm.grad, max(tol, 5e-4), errs)
+    for name, buf in m.named_buffers():
+        if "running" in name:
+            assert O.rel_err(buf.cpu(), torch.from_numpy(z["running/" + name])) < TOL_FP32
