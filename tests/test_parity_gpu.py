@@ -41,18 +41,30 @@ def _g_params(n, k, Q, G, qinj, gen, scale=1.0):
     return out
 
 
+def _oracle_grads(x, q, gp, qinj, dxg, dtype):
+    xx, qq = x.to(dtype).requires_grad_(True), q.to(dtype).requires_grad_(True)
+    g = [(w.to(dtype).requires_grad_(True), b.to(dtype).requires_grad_(True)) for w, b in gp]
+    xg = O.g_mlp_dense(xx, qq, g, qinj)
+    xg.backward(dxg.to(dtype))
+    out = {"xg": xg.detach(), "dx": xx.grad, "dq": qq.grad}
+    for l in range(4):
+        out[f"dW{l}"], out[f"db{l}"] = g[l][0].grad, g[l][1].grad
+    return out
+
+
 def _relation_case(name, precision, tol):
+    """CUDA vs the fp64 oracle.  A ReLU pre-activation that lands within round-off of zero flips its
+    gradient mask under ANY fp32 evaluation order (the fp32 CPU oracle shows the same), so each tensor's
+    tolerance is floored at 4x the fp32-oracle-vs-fp64-oracle distance measured on the same inputs."""
     B, n, k, Q, G, qinj = SHAPES[name]
-    gen = torch.Generator().manual_seed(hash(name) % 1000)
+    gen = torch.Generator().manual_seed(sorted(SHAPES).index(name) + 11)
     x = torch.randn(B, n, k, generator=gen)
     q = torch.randn(B, Q, generator=gen)
     gp = _g_params(n, k, Q, G, qinj, gen, scale=2.0)
     dxg = torch.randn(B, G, generator=gen)
-    # oracle (fp64 for a clean yardstick)
-    x64, q64 = x.double().requires_grad_(True), q.double().requires_grad_(True)
-    gp64 = [(w.double().requires_grad_(True), b.double().requires_grad_(True)) for w, b in gp]
-    xg_ref = O.g_mlp_dense(x64, q64, gp64, qinj)
-    xg_ref.backward(dxg.double())
+    ref = _oracle_grads(x, q, gp, qinj, dxg, torch.float64)
+    ref32 = _oracle_grads(x, q, gp, qinj, dxg, torch.float32)
+    floor = {k_: 4 * O.rel_err(ref32[k_], ref[k_]) for k_ in ref}
     # CUDA
     xc, qc = x.to(DEV).requires_grad_(True), q.to(DEV).requires_grad_(True)
     wb = []
@@ -60,13 +72,12 @@ def _relation_case(name, precision, tol):
         wb += [w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)]
     xg = ops.RelationFunction.apply(xc, qc, qinj, precision, *wb)
     xg.backward(dxg.to(DEV))
-    errs = {"xg": O.rel_err(xg.detach().cpu(), xg_ref.detach())}
-    errs["dx"] = O.rel_err(xc.grad.cpu(), x64.grad)
-    errs["dq"] = O.rel_err(qc.grad.cpu(), q64.grad)
+    got = {"xg": xg.detach(), "dx": xc.grad, "dq": qc.grad}
     for l in range(4):
-        errs[f"dW{l}"] = O.rel_err(wb[2 * l].grad.cpu(), gp64[l][0].grad)
-        errs[f"db{l}"] = O.rel_err(wb[2 * l + 1].grad.cpu(), gp64[l][1].grad)
-    bad = {k_: v for k_, v in errs.items() if not v <= tol}
+        got[f"dW{l}"], got[f"db{l}"] = wb[2 * l].grad, wb[2 * l + 1].grad
+    errs = {k_: O.rel_err(got[k_].cpu(), ref[k_]) for k_ in ref}
+    print(name, precision, {k_: f"{v:.1e}" for k_, v in errs.items()})
+    bad = {k_: (v, floor[k_]) for k_, v in errs.items() if not v <= max(tol, floor[k_])}
     assert not bad, (name, precision, bad)
     return errs
 
