@@ -42,8 +42,11 @@ def _g_params(n, k, Q, G, qinj, gen, scale=1.0):
 
 
 def _oracle_grads(x, q, gp, qinj, dxg, dtype):
-    xx, qq = x.to(dtype).requires_grad_(True), q.to(dtype).requires_grad_(True)
-    g = [(w.to(dtype).requires_grad_(True), b.to(dtype).requires_grad_(True)) for w, b in gp]
+    def leaf(t):
+        return t.detach().clone().to(dtype).requires_grad_(True)
+
+    xx, qq = leaf(x), leaf(q)
+    g = [(leaf(w), leaf(b)) for w, b in gp]
     xg = O.g_mlp_dense(xx, qq, g, qinj)
     xg.backward(dxg.to(dtype))
     out = {"xg": xg.detach(), "dx": xx.grad, "dq": qq.grad}
