@@ -73,3 +73,29 @@ def golden_grad_check(z, name, grad, tol, errs):
     l2 = float(g.double().norm())
     assert abs(l2 - float(z[key + "l2"])) <= tol * max(float(z[key + "l2"]), floor, 1e-30) * 4, \
         (name, l2, float(z[key + "l2"]))
+
+
+_grad_cache = {}
+
+
+def oracle_train_grads(stem):
+    """fp64 oracle gradients of a *_train fixture plus, per tensor, the conditioning floor: the distance
+    between the fp32 and fp64 oracle on the same inputs (ReLU-mask flips at |z| ~ round-off make some
+    cases ill-conditioned for ANY fp32 evaluation order).  Cached per process."""
+    if stem in _grad_cache:
+        return _grad_cache[stem]
+    import torch.nn.functional as F
+
+    z = load_npz(stem + "_train")
+    hyp, p = case_params(stem)
+    img, qst = case_inputs(z)
+    lab = torch.from_numpy(z["label"])
+    mask = torch.from_numpy(z["dropout_mask"])
+    grads = {}
+    for dt in (torch.float64, torch.float32):
+        leaves = {k: v.to(dt).clone().requires_grad_("running" not in k) for k, v in p.items()}
+        F.nll_loss(O.rn_forward(leaves, hyp, img.to(dt), qst, True, mask), lab).backward()
+        grads[dt] = {k: v.grad for k, v in leaves.items() if v.grad is not None}
+    floor = {k: O.rel_err(grads[torch.float32][k], g) for k, g in grads[torch.float64].items()}
+    _grad_cache[stem] = (grads[torch.float64], floor)
+    return _grad_cache[stem]

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 import relationnetworks_clevr_b200 as R
 from oracle import rn_oracle as O
 from relationnetworks_clevr_b200 import ops
-from tests.golden_util import CASES, case_inputs, case_params, golden_grad_check, load_npz
+from tests.golden_util import CASES, case_inputs, case_params, load_npz, oracle_train_grads
 
 pytestmark = pytest.mark.gpu
 
@@ -238,11 +238,21 @@ def test_model_train_step_matches_reference_golden(stem, precision):
     loss.backward()
     tol = TOL_FP32 if precision == "fp32" else TOL_PARITY
     assert O.rel_err(logp.detach().cpu(), torch.from_numpy(z["logp"])) < tol
-    assert abs(float(loss) - float(z["loss"])) < tol * max(1.0, abs(float(z["loss"])))
-    errs = {}
+    assert abs(float(loss.detach()) - float(z["loss"])) < tol * max(1.0, abs(float(z["loss"])))
+    # gradients: against the fp64 oracle (itself pinned to the reference's gradients by
+    # tests/test_oracle_golden.py), tolerance floored at 4x the fp32-oracle conditioning noise
+    ref, floor = oracle_train_grads(stem)
+    bad = {}
     for name, prm in m.named_parameters():
-        if f"grad/{name}/l2" in z.files:
-            golden_grad_check(z, name, prm.grad, max(tol, 5e-4), errs)
+        if name not in ref:
+            continue
+        if name.startswith("conv.conv") and name.endswith("bias"):
+            assert float(prm.grad.abs().max()) == 0.0       # exactly zero under batch statistics
+            continue
+        err = O.rel_err(prm.grad.cpu(), ref[name])
+        if err > max(tol, 4 * floor[name]):
+            bad[name] = (err, floor[name])
+    assert not bad, bad
     for name, buf in m.named_buffers():
         if "running" in name:
             assert O.rel_err(buf.cpu(), torch.from_numpy(z["running/" + name])) < TOL_FP32
