@@ -87,21 +87,29 @@ __global__ void pack_weights_kernel(PackArgs args, __half* __restrict__ out, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward kernel
+// chain kernel: forward (eval / training) and data-gradient share one pipeline skeleton
 // ------------------------------------------------------------------------------------------------
-struct FwdParams {
-  const float* U;                  // [B, n, 256]
-  const float* Vb;                 // [B, n, 256]  (V + beta0)
-  const float* bias[kTcLayers];    // layer l+1 bias; element [b * bias_stride + col]
-  long long bias_stride[kTcLayers];
-  const __half* wpack;             // [3][2][4] x 32 KB
-  float* xg_part;                  // [tiles][4][256]
-  __half* saveH;                   // [tiles][2] x 64 KB (H2, H3 operand images) or nullptr
-  uint32_t* masks;                 // [3][tiles][128][8] bit c of word w <-> column 32w+c (Z2, Z3, Z4 > 0) or nullptr
+enum ChainMode { kFwdEval = 0, kFwdTrain = 1, kDgrad = 2 };
+
+struct ChainParams {
+  const __half* wpack;             // [3][2][4] x 32 KB chunk images (forward: W; dgrad: W^T)
   int n;
   int tiles_per_sample;
   int num_tiles;
   int passes;                      // 2 = parity (hi + lo), 1 = fast
+  // forward
+  const float* U;                  // [B, n, 256]
+  const float* Vb;                 // [B, n, 256]  (V + beta0)
+  const float* bias[kTcLayers];    // g layer l+1 bias; element [b * bias_stride + col]
+  long long bias_stride[kTcLayers];
+  float* xg_part;                  // [tiles][4][256]
+  __half* saveH;                   // [tiles][3] x 64 KB operand images H1, H2, H3 (training)
+  uint32_t* masks;                 // [4][tiles][128][8] sign bits of Z1..Z4 (training; read by dgrad)
+  // dgrad
+  const float* dxg;                // [B, 256]
+  const float* scale;              // [0] = S (power of two applied to dxg), [1] = 1/S
+  __half* dZ;                      // [tiles][4] x 64 KB images dZ1..dZ4 (scaled by S)
+  float* colpart;                  // [3][tiles][4][256] column sums of dZ2, dZ3, dZ4 per (tile, row quarter)
 };
 
 struct Bars {
@@ -116,9 +124,27 @@ __device__ __forceinline__ int tiles_of_cta(int num_tiles) {
   return (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 }
 
-// H1 rows of one tile -> swizzled fp16 A operand.  Warp `q` (0..3) of the warpgroup owns rows [32q, 32q+32).
-// Lane mapping: 4 rows x 8 sixteen-byte groups per step -> 256-byte coalesced reads of U, conflict-free STS.
-__device__ __forceinline__ void generate_h1(const FwdParams& p, int tile, char* a_tile, int q, int lane) {
+// Sum x[0..31] over the 32 lanes (rows) of the warp: afterwards lane L holds the total of element L.
+__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int e = 0; e < off; ++e) {
+      const float send = upper ? x[e] : x[e + off];
+      const float keep = upper ? x[e + off] : x[e];
+      x[e] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return x[0];
+}
+
+// Forward generation: H1 rows of one tile -> swizzled fp16 A operand (the pair matrix never exists anywhere).
+// Warp `q` (0..3) of the warpgroup owns rows [32q, 32q+32).  Lane mapping: 4 rows x 8 sixteen-byte groups per
+// step -> 256-byte coalesced reads of U, conflict-free STS.  M1 sign bits use the permuted layout
+// word j = (col % 64) / 8, bit = (col / 64) * 8 + col % 8.
+template <bool SAVE>
+__device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
   const int b = tile / p.tiles_per_sample;
   const int p0 = (tile % p.tiles_per_sample) * kTileM;
   const float* Ub = p.U + (size_t)b * p.n * kG;
@@ -131,22 +157,83 @@ __device__ __forceinline__ void generate_h1(const FwdParams& p, int tile, char* 
     const int a = pr / p.n, c = pr - a * p.n;
     const float4* up = reinterpret_cast<const float4*>(Ub + (size_t)c * kG + j * 8);
     const float4* vp = reinterpret_cast<const float4*>(Vb + (size_t)a * kG + j * 8);
+    uint32_t bits = 0;
 #pragma unroll
     for (int kc = 0; kc < kNKC; ++kc) {
       const float4 u0 = __ldg(up + kc * 16), u1 = __ldg(up + kc * 16 + 1);
       const float4 v0 = __ldg(vp + kc * 16), v1 = __ldg(vp + kc * 16 + 1);
+      const float h[8] = {fmaxf(u0.x + v0.x, 0.f), fmaxf(u0.y + v0.y, 0.f), fmaxf(u0.z + v0.z, 0.f), fmaxf(u0.w + v0.w, 0.f),
+                          fmaxf(u1.x + v1.x, 0.f), fmaxf(u1.y + v1.y, 0.f), fmaxf(u1.z + v1.z, 0.f), fmaxf(u1.w + v1.w, 0.f)};
+      if (SAVE) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bits |= (h[e] > 0.f ? 1u : 0u) << (kc * 8 + e);
+      }
       uint4 o;
-      o.x = pack_half2(fmaxf(u0.x + v0.x, 0.f), fmaxf(u0.y + v0.y, 0.f));
-      o.y = pack_half2(fmaxf(u0.z + v0.z, 0.f), fmaxf(u0.w + v0.w, 0.f));
-      o.z = pack_half2(fmaxf(u1.x + v1.x, 0.f), fmaxf(u1.y + v1.y, 0.f));
-      o.w = pack_half2(fmaxf(u1.z + v1.z, 0.f), fmaxf(u1.w + v1.w, 0.f));
+      o.x = pack_half2(h[0], h[1]);
+      o.y = pack_half2(h[2], h[3]);
+      o.z = pack_half2(h[4], h[5]);
+      o.w = pack_half2(h[6], h[7]);
       *reinterpret_cast<uint4*>(a_tile + kc * kAChunk + sw128_offset(row, j * 8)) = o;
     }
+    if (SAVE) p.masks[((size_t)tile * kTileM + row) * 8 + j] = bits;      // masks[0] = M1
   }
 }
 
-template <bool SAVE>
-__global__ void __launch_bounds__(kFwdThreads, 1) rn_g_fwd_kernel(const FwdParams p) {
+// Backward generation: dZ4[r, :] = S * dxg[b, :] where Z4[r, :] > 0 -> swizzled fp16 A operand, plus the
+// per-(tile, quarter) column sums of dZ4 (for db3).  Same lane mapping as generate_h1.
+__device__ __forceinline__ void generate_dz4(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
+  const int b = tile / p.tiles_per_sample;
+  const int sub = lane >> 3, j = lane & 7;
+  const float S = __ldg(p.scale);
+  float d[kNKC][8], acc[kNKC][8];
+#pragma unroll
+  for (int kc = 0; kc < kNKC; ++kc) {
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + kc * 64 + j * 8));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + kc * 64 + j * 8 + 4));
+    d[kc][0] = d0.x * S; d[kc][1] = d0.y * S; d[kc][2] = d0.z * S; d[kc][3] = d0.w * S;
+    d[kc][4] = d1.x * S; d[kc][5] = d1.y * S; d[kc][6] = d1.z * S; d[kc][7] = d1.w * S;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[kc][e] = 0.f;
+  }
+  const uint32_t* m4 = p.masks + ((size_t)3 * p.num_tiles + tile) * kTileM * 8;
+#pragma unroll 2
+  for (int g = 0; g < 8; ++g) {
+    const int row = q * 32 + g * 4 + sub;
+    // cols kc*64 + j*8 + e live in word kc*2 + (j >> 2), bits (j & 3)*8 + e
+#pragma unroll
+    for (int kc = 0; kc < kNKC; ++kc) {
+      const uint32_t word = __ldg(m4 + (size_t)row * 8 + kc * 2 + (j >> 2));
+      const uint32_t byte = (word >> ((j & 3) * 8)) & 0xffu;
+      float h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        h[e] = ((byte >> e) & 1u) ? d[kc][e] : 0.f;
+        acc[kc][e] += h[e];
+      }
+      uint4 o;
+      o.x = pack_half2(h[0], h[1]);
+      o.y = pack_half2(h[2], h[3]);
+      o.z = pack_half2(h[4], h[5]);
+      o.w = pack_half2(h[6], h[7]);
+      *reinterpret_cast<uint4*>(a_tile + kc * kAChunk + sw128_offset(row, j * 8)) = o;
+    }
+  }
+  // reduce over the 4 sub-rows (lane bits 3 and 4); lanes with sub == 0 store 32 columns each
+  float* part = p.colpart + (((size_t)2 * p.num_tiles + tile) * 4 + q) * kG;
+#pragma unroll
+  for (int kc = 0; kc < kNKC; ++kc)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = acc[kc][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (sub == 0) part[kc * 64 + j * 8 + e] = v;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainParams p) {
+  constexpr bool SAVE = MODE != kFwdEval;        // training forward and dgrad stream operand images to HBM
   extern __shared__ char smem_raw[];
   char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars* bars = reinterpret_cast<Bars*>(smem + kSmemBar);
@@ -177,17 +264,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_fwd_kernel(const FwdParam
       uint32_t stage = 0, phase = 0;
       for (int r = 0; 2 * r < my_tiles; ++r) {
         const int nslots = (2 * r + 1 < my_tiles) ? 2 : 1;
-        for (int layer = 0; layer < kTcLayers; ++layer)
+        for (int layer = 0; layer < kTcLayers; ++layer) {
+          const int img_layer = MODE == kDgrad ? kTcLayers - 1 - layer : layer;    // dgrad walks W3^T, W2^T, W1^T
           for (int s = 0; s < nslots; ++s)
             for (int pass = 0; pass < p.passes; ++pass)
               for (int kc = 0; kc < kNKC; ++kc) {
                 mbar_wait(smem_u32(&bars->w_empty[stage]), phase ^ 1);
                 const uint32_t full = smem_u32(&bars->w_full[stage]);
                 mbar_expect_tx(full, kWChunk);
-                const char* src = reinterpret_cast<const char*>(p.wpack) + ((size_t)(layer * 2 + pass) * kNKC + kc) * kWChunk;
+                const char* src = reinterpret_cast<const char*>(p.wpack) + ((size_t)(img_layer * 2 + pass) * kNKC + kc) * kWChunk;
                 bulk_g2s(smem_u32(smem + kSmemW + stage * kWChunk), src, kWChunk, full);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
               }
+        }
       }
     }
   } else if (warp == 1) {
@@ -225,7 +314,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_fwd_kernel(const FwdParam
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue warpgroups =================
+    // ================= generation / epilogue warpgroups =================
     const int s = (warp - 4) >> 2;             // tile slot
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
@@ -235,104 +324,145 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_fwd_kernel(const FwdParam
     const uint32_t acc_full = smem_u32(&bars->acc_full[s]);
     const uint32_t bar_id = 1 + s;
     uint32_t acc_phase = 0;
+
+    // stream the freshly written operand image of this slot to HBM (one elected thread, bulk async store)
+    auto store_image = [&](char* dst) {
+      named_bar_sync(bar_id, 128);              // whole image written and fenced by every thread
+      if (wg_tid == 0) {
+        bulk_s2g(dst, smem_u32(a_tile), kATile);
+        bulk_commit();
+      }
+    };
+    // before overwriting the A buffer: the previous image store must have finished READING it
+    auto wait_image_read = [&]() {
+      if (wg_tid == 0) bulk_wait_read0();
+      named_bar_sync(bar_id, 128);
+    };
+
     for (int i = s; i < my_tiles; i += 2) {
       const int tile = blockIdx.x + i * gridDim.x;
       const int b = tile / p.tiles_per_sample;
-      if (SAVE) {      // the previous tile's H3 image may still be streaming out of this A buffer
-        if (wg_tid == 0) bulk_wait_read0();
-        named_bar_sync(bar_id, 128);
-      }
-      generate_h1(p, tile, a_tile, q, lane);
+      if (SAVE) wait_image_read();
+      if (MODE == kDgrad) generate_dz4(p, tile, a_tile, q, lane);
+      else generate_h1<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
       fence_proxy_async_smem();
+      if (MODE == kFwdTrain) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile);
+      if (MODE == kDgrad) store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + 3) * kATile);
       mbar_arrive(a_full);
+
       for (int layer = 0; layer < kTcLayers; ++layer) {
-        mbar_wait(acc_full, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after_sync();
-        const float* bias = p.bias[layer] + (size_t)b * p.bias_stride[layer];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * kG;
-        uint32_t* mrow = SAVE ? p.masks + (((size_t)layer * p.num_tiles + tile) * kTileM + row) * 8 : nullptr;
-        if (layer < kTcLayers - 1) {
-          if (SAVE) {
-            if (wg_tid == 0) bulk_wait_read0();
-            named_bar_sync(bar_id, 128);
-          }
-          uint32_t mw[8];
+        if (MODE != kDgrad) {
+          // ---------------- forward epilogue ----------------
+          const float* bias = p.bias[layer] + (size_t)b * p.bias_stride[layer];
+          uint32_t* mrow = SAVE ? p.masks + (((size_t)(layer + 1) * p.num_tiles + tile) * kTileM + row) * 8 : nullptr;
+          mbar_wait(acc_full, acc_phase);
+          acc_phase ^= 1;
+          tc_fence_after_sync();
+          if (layer < kTcLayers - 1) {
+            if (SAVE) wait_image_read();
+            uint32_t mw[8];
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            uint32_t r[32];
-            tmem_ld32(taddr + cc * 32, r);
-            tmem_ld_wait();
-            uint32_t bits = 0;
+            for (int cc = 0; cc < 8; ++cc) {
+              uint32_t r[32];
+              tmem_ld32(taddr + cc * 32, r);
+              tmem_ld_wait();
+              uint32_t bits = 0;
 #pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              float v[8];
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + g4 * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + g4 * 8 + 4));
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              for (int g4 = 0; g4 < 4; ++g4) {
+                float v[8];
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + g4 * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + g4 * 8 + 4));
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                v[e] = fmaxf(__uint_as_float(r[g4 * 8 + e]) + bb[e], 0.f);
-                bits |= (v[e] > 0.f ? 1u : 0u) << (g4 * 8 + e);
+                for (int e = 0; e < 8; ++e) {
+                  v[e] = fmaxf(__uint_as_float(r[g4 * 8 + e]) + bb[e], 0.f);
+                  bits |= (v[e] > 0.f ? 1u : 0u) << (g4 * 8 + e);
+                }
+                uint4 o;
+                o.x = pack_half2(v[0], v[1]);
+                o.y = pack_half2(v[2], v[3]);
+                o.z = pack_half2(v[4], v[5]);
+                o.w = pack_half2(v[6], v[7]);
+                const int col = cc * 32 + g4 * 8;
+                *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + sw128_offset(row, col & 63)) = o;
               }
-              uint4 o;
-              o.x = pack_half2(v[0], v[1]);
-              o.y = pack_half2(v[2], v[3]);
-              o.z = pack_half2(v[4], v[5]);
-              o.w = pack_half2(v[6], v[7]);
-              const int col = cc * 32 + g4 * 8;
-              *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + sw128_offset(row, col & 63)) = o;
+              mw[cc] = bits;
             }
-            mw[cc] = bits;
-          }
-          if (SAVE) {
-            *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-            *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
-          }
-          fence_proxy_async_smem();
-          if (SAVE) {
-            named_bar_sync(bar_id, 128);          // whole operand image written
-            if (wg_tid == 0) {
-              bulk_s2g(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 2 + layer) * kATile, smem_u32(a_tile), kATile);
-              bulk_commit();
+            if (SAVE) {
+              *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+              *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
             }
+            fence_proxy_async_smem();
+            if (SAVE) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + layer + 1) * kATile);
+            tc_fence_before_sync();
+            mbar_arrive(a_full);
+          } else {
+            // last layer: ReLU + pair-sum.  Column sums over this warp's 32 rows by shuffle transpose-reduce.
+            float* part = p.xg_part + ((size_t)tile * 4 + q) * kG;
+            uint32_t mw[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              uint32_t r[32];
+              tmem_ld32(taddr + cc * 32, r);
+              tmem_ld_wait();
+              float x[32];
+              uint32_t bits = 0;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                x[e] = fmaxf(__uint_as_float(r[e]) + __ldg(bias + cc * 32 + e), 0.f);
+                bits |= (x[e] > 0.f ? 1u : 0u) << e;
+              }
+              mw[cc] = bits;
+              part[cc * 32 + lane] = warp_transpose_sum(x, lane);     // lane L holds the sum of column cc*32 + L
+            }
+            if (SAVE) {
+              *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+              *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+            }
+            tc_fence_before_sync();
           }
-          tc_fence_before_sync();
-          mbar_arrive(a_full);
         } else {
-          // last layer: ReLU + pair-sum.  Column sums over this warp's 32 rows by shuffle transpose-reduce.
-          float* part = p.xg_part + ((size_t)tile * 4 + q) * kG;
-          uint32_t mw[8];
+          // ---------------- data-gradient epilogue: dZ_l = dH_l .* (Z_l > 0), l = 3 - layer ----------------
+          const int l = kTcLayers - layer;                // 3, 2, 1
+          const uint32_t* mrow = p.masks + (((size_t)(l - 1) * p.num_tiles + tile) * kTileM + row) * 8;
+          const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow));
+          const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow) + 1);
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          mbar_wait(acc_full, acc_phase);
+          acc_phase ^= 1;
+          tc_fence_after_sync();
+          wait_image_read();
+          float* part = l >= 2 ? p.colpart + (((size_t)(l - 2) * p.num_tiles + tile) * 4 + q) * kG : nullptr;
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
             uint32_t r[32];
             tmem_ld32(taddr + cc * 32, r);
             tmem_ld_wait();
             float x[32];
-            uint32_t bits = 0;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              x[e] = fmaxf(__uint_as_float(r[e]) + __ldg(bias + cc * 32 + e), 0.f);
-              bits |= (x[e] > 0.f ? 1u : 0u) << e;
+              // Z2..Z4 masks: word cc, bit e.  Z1 mask (l == 1): permuted layout written by generate_h1.
+              const uint32_t bit = (l == 1) ? (mw[(cc & 1) * 4 + (e >> 3)] >> ((cc >> 1) * 8 + (e & 7))) & 1u
+                                            : (mw[cc] >> e) & 1u;
+              x[e] = bit ? __uint_as_float(r[e]) : 0.f;
             }
-            mw[cc] = bits;
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-              const bool upper = (lane & off) != 0;
-#pragma unroll
-              for (int e = 0; e < off; ++e) {
-                const float send = upper ? x[e] : x[e + off];
-                const float keep = upper ? x[e + off] : x[e];
-                x[e] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-              }
+            for (int g4 = 0; g4 < 4; ++g4) {
+              uint4 o;
+              o.x = pack_half2(x[g4 * 8 + 0], x[g4 * 8 + 1]);
+              o.y = pack_half2(x[g4 * 8 + 2], x[g4 * 8 + 3]);
+              o.z = pack_half2(x[g4 * 8 + 4], x[g4 * 8 + 5]);
+              o.w = pack_half2(x[g4 * 8 + 6], x[g4 * 8 + 7]);
+              const int col = cc * 32 + g4 * 8;
+              *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + sw128_offset(row, col & 63)) = o;
             }
-            part[cc * 32 + lane] = x[0];           // lane L holds the sum of column cc*32 + L
+            if (l >= 2) part[cc * 32 + lane] = warp_transpose_sum(x, lane);
           }
-          if (SAVE) {
-            *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-            *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
-          }
+          fence_proxy_async_smem();
+          store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + (l - 1)) * kATile);
           tc_fence_before_sync();
+          if (layer < kTcLayers - 1) mbar_arrive(a_full);
         }
       }
     }
@@ -345,21 +475,205 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_fwd_kernel(const FwdParam
 }
 
 // ------------------------------------------------------------------------------------------------
+// weight-gradient kernel: dW_l[o][i] = sum_rows dZ_{l+1}[r][o] * H_l[r][i]
+// Both operands are the swizzled tile images the chain kernels streamed to HBM, read here as MN-major UMMA
+// operands (A = dZ^T, B = H).  One 256x256 fp32 accumulator (two M=128 halves = all 512 TMEM columns) stays
+// resident for the CTA's whole tile range; per-CTA partials are summed by a fixed-order reduce kernel.
+//   warp 0: bulk-copy producer (half tiles: 64 rows x 256 cols of each operand = 64 KB per stage, 3 stages)
+//   warp 1: MMA issuer (M128 x N256 x K16, 8 per stage)      warps 2-5: final TMEM -> global epilogue
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgThreads = 192;
+constexpr int kWgStageBytes = 65536;
+constexpr int kWgStages = 3;
+constexpr int kWgSmemBar = kWgStages * kWgStageBytes;
+constexpr int kWgSmemLaunch = kWgSmemBar + 128 + 1024;
+constexpr uint32_t kIdescWgrad = idesc_f16(kTileM, kG, 1, 1);
+
+struct WgradParams {
+  const char* dZ;          // image of tile t at dZ + t * dz_stride
+  size_t dz_stride;
+  const char* H;
+  size_t h_stride;
+  float* partial;          // [grid][256][256]
+  int num_tiles;
+};
+
+struct WgBars {
+  uint64_t full[kWgStages];
+  uint64_t empty[kWgStages];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradParams p) {
+  extern __shared__ char smem_raw[];
+  char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  WgBars* bars = reinterpret_cast<WgBars*>(smem + kWgSmemBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = tiles_of_cta(p.num_tiles);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(smem_u32(&bars->full[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bars->done), 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const size_t tile = blockIdx.x + (size_t)i * gridDim.x;
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
+          const uint32_t full = smem_u32(&bars->full[stage]);
+          mbar_expect_tx(full, kWgStageBytes);
+          const uint32_t dst = smem_u32(smem + stage * kWgStageBytes);
+#pragma unroll
+          for (int c = 0; c < kNKC; ++c) {      // rows [64*half, 64*half+64) of column chunk c: 8 KB contiguous
+            bulk_g2s(dst + c * 8192, p.dZ + tile * p.dz_stride + c * kAChunk + half * 8192, 8192, full);
+            bulk_g2s(dst + 32768 + c * 8192, p.H + tile * p.h_stride + c * kAChunk + half * 8192, 8192, full);
+          }
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t accumulate = 0;
+      for (int i = 0; i < 2 * my_tiles; ++i) {
+        mbar_wait(smem_u32(&bars->full[stage]), phase);
+        tc_fence_after_sync();
+        const uint32_t base = smem_u32(smem + stage * kWgStageBytes);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // MN-major SWIZZLE_128B: LBO = stride between 64-element MN atoms (8 KB), SBO = between 8-row K groups
+            const uint64_t ad = smem_desc_sw128(base + (2 * h) * 8192 + k * 2048, 8192, 1024);
+            const uint64_t bd = smem_desc_sw128(base + 32768 + k * 2048, 8192, 1024);
+            mma_f16_ss(tmem_base + h * kG, ad, bd, kIdescWgrad, accumulate | (uint32_t)(k > 0));
+          }
+        accumulate = 1;
+        mma_commit(smem_u32(&bars->empty[stage]));
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(smem_u32(&bars->done));
+    }
+  } else {
+    // warps 2..5 -> TMEM lane quarters 2, 3, 0, 1
+    const int q = warp & 3;
+    mbar_wait(smem_u32(&bars->done), 0);
+    tc_fence_after_sync();
+    float* out = p.partial + (size_t)blockIdx.x * kG * kG;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h)
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * kG + cc * 32, r);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)(h * 128 + q * 32 + lane) * kG + cc * 32);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          dst[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
+                               __uint_as_float(r[4 * e + 3]));
+      }
+    tc_fence_before_sync();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// dW[o * ld + i] = scale[1] * sum_parts partial[part][o][i]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ dW, int ld,
+                                    const float* __restrict__ scale) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= kG * kG) return;
+  float v = 0.f;
+  for (int pidx = 0; pidx < nparts; ++pidx) v += partial[(size_t)pidx * kG * kG + idx];
+  dW[(size_t)(idx / kG) * ld + idx % kG] = v * scale[1];
+}
+
+// S = 2^k with max|dxg| * S in (4, 8]: keeps the fp16 gradient operands in the normal range
+__global__ void grad_scale_kernel(const float* __restrict__ dxg, int n, float* __restrict__ scale) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(dxg[i]));
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+    float S = 1.f;
+    if (m > 0.f && isfinite(m)) S = exp2f(3.f - ceilf(log2f(m)));
+    scale[0] = S;
+    scale[1] = 1.f / S;
+  }
+}
+
+__global__ void scale_inplace_kernel(float* __restrict__ x, long long n, const float* __restrict__ scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= scale[1];
+}
+
+// dU[b, c, :] = (1/S) sum_a dZ1[(a, c), :],  dV[b, a, :] = (1/S) sum_c dZ1[(a, c), :]   from the dZ1 tile images.
+// grid (B, 4 column chunks), block 256; each thread owns (object, 16-byte column group) accumulators and walks
+// the other pair index in a fixed order -> deterministic.
+__global__ void __launch_bounds__(256)
+dz1_reduce_kernel(const char* __restrict__ dZ, size_t tile_stride, float* __restrict__ dU, float* __restrict__ dV,
+                  const float* __restrict__ scale, int n, int tiles_per_sample) {
+  const int b = blockIdx.x, kc = blockIdx.y;
+  const float inv = scale[1];
+  const char* base = dZ + (size_t)b * tiles_per_sample * tile_stride + (size_t)kc * kAChunk;
+  for (int pass = 0; pass < 2; ++pass) {
+    float* out = pass == 0 ? dU : dV;
+    for (int item = threadIdx.x; item < n * 8; item += 256) {
+      const int obj = item >> 3, j = item & 7;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int o = 0; o < n; ++o) {
+        const int pr = pass == 0 ? o * n + obj : obj * n + o;      // pair row a*n + c
+        const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)(pr / kTileM) * tile_stride +
+                                                        sw128_offset(pr % kTileM, j * 8));
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          acc[2 * e] += f.x;
+          acc[2 * e + 1] += f.y;
+        }
+      }
+      float* dst = out + ((size_t)b * n + obj) * kG + kc * 64 + j * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 bool tc_supported(const RelShape& s) {
   return s.G == kG && s.L == 4 && s.pairs % kTileM == 0 && s.qinj >= 0 && s.qinj < 4;
 }
 
+static size_t wpack_bytes() { return (size_t)kTcLayers * 2 * kNKC * kWChunk; }
+
 struct TcSaved {
   RelPre pre;
   __half* wpack;       // forward weight images
-  __half* saveH;
-  uint32_t* masks;
-  float* biases;       // [4][256] copy of the g biases (v1 backward recomputes the forward)
+  __half* saveH;       // [tiles][3] x 64 KB
+  uint32_t* masks;     // [4][tiles][128][8]
 };
-
-static size_t wpack_bytes() { return (size_t)kTcLayers * 2 * kNKC * kWChunk; }
 
 static TcSaved tc_carve_saved(const RelShape& s, void* saved, bool training) {
   Carver c(saved);
@@ -369,25 +683,68 @@ static TcSaved tc_carve_saved(const RelShape& s, void* saved, bool training) {
   o.pre.Qb = c.take<float>((size_t)s.B * s.G);
   o.wpack = reinterpret_cast<__half*>(c.take<char>(wpack_bytes()));
   const size_t tiles = s.rows / kTileM;
-  o.saveH = training ? reinterpret_cast<__half*>(c.take<char>(tiles * 2 * kATile)) : nullptr;
-  o.masks = training ? c.take<uint32_t>(tiles * kTcLayers * kTileM * 8) : nullptr;
-  o.biases = training ? c.take<float>(4 * kG) : nullptr;
+  o.saveH = training ? reinterpret_cast<__half*>(c.take<char>(tiles * 3 * kATile)) : nullptr;
+  o.masks = training ? c.take<uint32_t>(tiles * 4 * kTileM * 8) : nullptr;
   return o;
 }
 
 size_t tc_saved_bytes(const RelShape& s, bool training) {
   const size_t tiles = s.rows / kTileM;
   size_t b = 2 * round_up((size_t)s.B * s.n * s.G * 4, 256) + round_up((size_t)s.B * s.G * 4, 256) + round_up(wpack_bytes(), 256);
-  if (training) b += round_up(tiles * 2 * kATile, 256) + round_up(tiles * kTcLayers * kTileM * 8 * 4, 256) + 4 * kG * 4;
+  if (training) b += round_up(tiles * 3 * kATile, 256) + round_up(tiles * 4 * kTileM * 8 * 4, 256);
   return b;
+}
+
+struct TcBwdScratch {
+  float* scale;
+  __half* wpackT;
+  __half* dZ;          // [tiles][4] x 64 KB
+  float* colpart;      // [3][tiles][4][256]
+  float* partial;      // [grid][256][256]
+  float* delta;        // [3][B][256]
+  float* dU;
+  float* dV;
+};
+
+static TcBwdScratch tc_carve_bwd(const RelShape& s, void* scratch) {
+  Carver c(scratch);
+  TcBwdScratch o;
+  const size_t tiles = s.rows / kTileM;
+  o.scale = c.take<float>(64);
+  o.wpackT = reinterpret_cast<__half*>(c.take<char>(wpack_bytes()));
+  o.dZ = reinterpret_cast<__half*>(c.take<char>(tiles * 4 * kATile));
+  o.colpart = c.take<float>(tiles * 3 * 4 * kG);
+  o.partial = c.take<float>((size_t)256 * kG * kG);
+  o.delta = c.take<float>((size_t)3 * s.B * kG);
+  o.dU = c.take<float>((size_t)s.B * s.n * kG);
+  o.dV = c.take<float>((size_t)s.B * s.n * kG);
+  return o;
 }
 
 size_t tc_scratch_bytes(const RelShape& s, bool training) {
   const size_t tiles = s.rows / kTileM;
-  size_t fwd = round_up(tiles * 4 * kG * 4, 256);
-  // v1 backward: fp32 SIMT recompute + backward (to be replaced by the tcgen05 dgrad/wgrad kernels)
-  size_t bwd = training ? simt_saved_bytes(s, true) + simt_scratch_bytes(s, true) + round_up((size_t)s.B * s.G * 4, 256) : 0;
+  const size_t fwd = round_up(tiles * 4 * kG * 4, 256);
+  if (!training) return fwd;
+  size_t bwd = 256 + round_up(wpack_bytes(), 256) + round_up(tiles * 4 * kATile, 256) + round_up(tiles * 3 * 4 * kG * 4, 256) +
+               round_up((size_t)256 * kG * kG * 4, 256) + round_up((size_t)3 * s.B * kG * 4, 256) +
+               2 * round_up((size_t)s.B * s.n * kG * 4, 256);
   return fwd > bwd ? fwd : bwd;
+}
+
+static void fill_pack_args(const RelShape& s, const float* const* g_w, PackArgs& pa) {
+  for (int l = 0; l < kTcLayers; ++l) {
+    pa.w[l] = g_w[l + 1];
+    pa.ld[l] = s.fan_in(l + 1);
+  }
+}
+
+template <int MODE>
+static int launch_chain(const ChainParams& p, cudaStream_t st) {
+  const int grid = std::min(p.num_tiles, sm_count());
+  RN_CUDA(cudaFuncSetAttribute(rn_g_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+  rn_g_chain_kernel<MODE><<<grid, kFwdThreads, kSmemLaunch, st>>>(p);
+  RN_LAUNCH_CHECK("rn_g_chain_kernel");
+  return RN_OK;
 }
 
 int tc_relation_fwd(const RelShape& s, int precision, bool training, const float* x, const float* q,
@@ -395,18 +752,12 @@ int tc_relation_fwd(const RelShape& s, int precision, bool training, const float
                     cudaStream_t st) {
   TcSaved sv = tc_carve_saved(s, saved, training);
   RN_TRY(relation_pre(s, x, q, g_w, g_b, sv.pre, st));
-  if (training)
-    for (int l = 0; l < 4; ++l)
-      RN_CUDA(cudaMemcpyAsync(sv.biases + l * kG, g_b[l], kG * sizeof(float), cudaMemcpyDeviceToDevice, st));
   PackArgs pa;
-  for (int l = 0; l < kTcLayers; ++l) {
-    pa.w[l] = g_w[l + 1];
-    pa.ld[l] = s.fan_in(l + 1);
-  }
+  fill_pack_args(s, g_w, pa);
   pack_weights_kernel<<<cdiv(kTcLayers * kG * (kG / 8), 256), 256, 0, st>>>(pa, sv.wpack, 0);
   RN_LAUNCH_CHECK("pack_weights_kernel");
 
-  FwdParams p;
+  ChainParams p = {};
   p.U = sv.pre.U;
   p.Vb = sv.pre.Vb;
   for (int l = 0; l < kTcLayers; ++l) {
@@ -426,15 +777,8 @@ int tc_relation_fwd(const RelShape& s, int precision, bool training, const float
   p.tiles_per_sample = (int)(s.pairs / kTileM);
   p.num_tiles = (int)(s.rows / kTileM);
   p.passes = precision == RN_PRECISION_FAST ? 1 : 2;
-  const int grid = std::min(p.num_tiles, sm_count());
-  if (training) {
-    RN_CUDA(cudaFuncSetAttribute(rn_g_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
-    rn_g_fwd_kernel<true><<<grid, kFwdThreads, kSmemLaunch, st>>>(p);
-  } else {
-    RN_CUDA(cudaFuncSetAttribute(rn_g_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
-    rn_g_fwd_kernel<false><<<grid, kFwdThreads, kSmemLaunch, st>>>(p);
-  }
-  RN_LAUNCH_CHECK("rn_g_fwd_kernel");
+  if (training) RN_TRY(launch_chain<kFwdTrain>(p, st));
+  else RN_TRY(launch_chain<kFwdEval>(p, st));
   // x_g[b] = sum over the sample's tiles and the 4 row quarters (fixed order -> deterministic)
   RN_TRY(colsum(p.xg_part, xg, s.G, s.B, 1, (long long)p.tiles_per_sample * 4, 0, 1, p.tiles_per_sample * 4, st));
   return RN_OK;
@@ -443,16 +787,62 @@ int tc_relation_fwd(const RelShape& s, int precision, bool training, const float
 int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const float* x, const float* q,
                     const float* const* g_w, const void* saved, float* dx, float* dq, float* const* dg_w,
                     float* const* dg_b, void* scratch, cudaStream_t st) {
-  // v1: recompute the forward in fp32 with the SIMT kernels, then the SIMT backward.
-  (void)precision;
   TcSaved sv = tc_carve_saved(s, const_cast<void*>(saved), true);
-  const float* g_b[4] = {sv.biases, sv.biases + kG, sv.biases + 2 * kG, sv.biases + 3 * kG};
-  char* base = static_cast<char*>(scratch);
-  void* simt_saved = base;
-  void* simt_scratch = base + simt_saved_bytes(s, true);
-  float* xg_tmp = reinterpret_cast<float*>(base + simt_saved_bytes(s, true) + simt_scratch_bytes(s, true));
-  RN_TRY(simt_relation_fwd(s, true, x, q, g_w, g_b, xg_tmp, simt_saved, simt_scratch, st));
-  return simt_relation_bwd(s, dxg, x, q, g_w, simt_saved, dx, dq, dg_w, dg_b, simt_scratch, st);
+  TcBwdScratch ws = tc_carve_bwd(s, scratch);
+  const int tps = (int)(s.pairs / kTileM);
+  const int tiles = (int)(s.rows / kTileM);
+
+  grad_scale_kernel<<<1, 1024, 0, st>>>(dxg, s.B * s.G, ws.scale);
+  RN_LAUNCH_CHECK("grad_scale_kernel");
+  PackArgs pa;
+  fill_pack_args(s, g_w, pa);
+  pack_weights_kernel<<<cdiv(kTcLayers * kG * (kG / 8), 256), 256, 0, st>>>(pa, ws.wpackT, 1);
+  RN_LAUNCH_CHECK("pack_weights_kernel");
+
+  // data gradient chain: dZ4 -> dZ3 -> dZ2 -> dZ1 (images to HBM), column sums of dZ2..dZ4
+  ChainParams p = {};
+  p.wpack = ws.wpackT;
+  p.n = s.n;
+  p.tiles_per_sample = tps;
+  p.num_tiles = tiles;
+  p.passes = precision == RN_PRECISION_FAST ? 1 : 2;
+  p.masks = sv.masks;
+  p.dxg = dxg;
+  p.scale = ws.scale;
+  p.dZ = ws.dZ;
+  p.colpart = ws.colpart;
+  RN_TRY(launch_chain<kDgrad>(p, st));
+
+  // weight gradients of g layers 1..3: dW_l = dZ_{l+1}^T H_l
+  const int wgrid = std::min(tiles, sm_count());
+  RN_CUDA(cudaFuncSetAttribute(rn_g_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLaunch));
+  for (int l = 1; l <= kTcLayers; ++l) {
+    WgradParams wp;
+    wp.dZ = reinterpret_cast<const char*>(ws.dZ) + (size_t)l * kATile;            // dZ_{l+1}
+    wp.dz_stride = (size_t)4 * kATile;
+    wp.H = reinterpret_cast<const char*>(sv.saveH) + (size_t)(l - 1) * kATile;    // H_l
+    wp.h_stride = (size_t)3 * kATile;
+    wp.partial = ws.partial;
+    wp.num_tiles = tiles;
+    rn_g_wgrad_kernel<<<wgrid, kWgThreads, kWgSmemLaunch, st>>>(wp);
+    RN_LAUNCH_CHECK("rn_g_wgrad_kernel");
+    wgrad_reduce_kernel<<<cdiv(kG * kG, 256), 256, 0, st>>>(ws.partial, wgrid, dg_w[l], s.fan_in(l), ws.scale);
+    RN_LAUNCH_CHECK("wgrad_reduce_kernel");
+    // bias gradient and question-injection gradients from the column sums of dZ_{l+1}
+    float* delta = ws.delta + (size_t)(l - 1) * s.B * kG;
+    RN_TRY(colsum(ws.colpart + (size_t)(l - 1) * tiles * 4 * kG, delta, kG, s.B, 1, (long long)tps * 4, 0, 1, tps * 4, st));
+    const long long nd = (long long)s.B * kG;
+    scale_inplace_kernel<<<cdiv(nd, 256), 256, 0, st>>>(delta, nd, ws.scale);
+    RN_LAUNCH_CHECK("scale_inplace_kernel");
+    RN_TRY(colsum(delta, dg_b[l], kG, 1, 1, 0, 0, 1, s.B, st));
+    if (l == s.qinj) RN_TRY(relation_qinj_bwd(s, l, q, g_w, delta, dq, dg_w, st));
+  }
+
+  // layer 0: dU / dV from the dZ1 images, then the small fp32 products
+  dz1_reduce_kernel<<<dim3(s.B, kNKC), 256, 0, st>>>(reinterpret_cast<const char*>(ws.dZ), (size_t)4 * kATile, ws.dU,
+                                                      ws.dV, ws.scale, s.n, tps);
+  RN_LAUNCH_CHECK("dz1_reduce_kernel");
+  return relation_layer0_bwd(s, x, q, g_w, ws.dU, ws.dV, ws.delta, dx, dq, dg_w, dg_b, st);
 }
 
 }  // namespace rn
