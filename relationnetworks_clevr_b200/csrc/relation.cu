@@ -52,7 +52,7 @@ int relation_qinj_bwd(const RelShape& s, int l, const float* q, const float* con
 
 int relation_layer0_bwd(const RelShape& s, const float* x, const float* q, const float* const* g_w, const float* dU,
                         const float* dV, float* delta, float* dx, float* dq, float* const* dg_w,
-                        float* const* dg_b, cudaStream_t st) {
+                        float* const* dg_b, float* ws, size_t ws_floats, cudaStream_t st) {
   const int fan0 = s.fan_in(0);
   GemmEpilogue none, acc;
   acc.beta = 1.f;
@@ -60,8 +60,8 @@ int relation_layer0_bwd(const RelShape& s, const float* x, const float* q, const
   RN_TRY(colsum(dV, delta, s.G, s.B, 1, s.n, 0, 1, s.n, st));
   RN_TRY(colsum(delta, dg_b[0], s.G, 1, 1, 0, 0, 1, s.B, st));
   // dW0c = dU^T X, dW0a = dV^T X  (sum over batch and objects)
-  RN_TRY(sgemm(true, false, s.G, s.k, s.B * s.n, dU, s.G, x, s.k, dg_w[0], fan0, none, st));
-  RN_TRY(sgemm(true, false, s.G, s.k, s.B * s.n, dV, s.G, x, s.k, dg_w[0] + s.k, fan0, none, st));
+  RN_TRY(sgemm(true, false, s.G, s.k, s.B * s.n, dU, s.G, x, s.k, dg_w[0], fan0, none, st, ws, ws_floats));
+  RN_TRY(sgemm(true, false, s.G, s.k, s.B * s.n, dV, s.G, x, s.k, dg_w[0] + s.k, fan0, none, st, ws, ws_floats));
   if (s.qinj == 0) RN_TRY(relation_qinj_bwd(s, 0, q, g_w, delta, dq, dg_w, st));
   // dX = dU W0c + dV W0a
   RN_TRY(sgemm(false, false, s.B * s.n, s.k, s.G, dU, s.G, g_w[0], fan0, dx, s.k, none, st));
@@ -201,7 +201,7 @@ int simt_relation_bwd(const RelShape& s, const float* dxg, const float* x, const
   // dZ is dZ1 [B, a, c, G]: dU[b,c] = sum_a, dV[b,a] = sum_c
   RN_TRY(colsum(dZ, dU, s.G, s.B, s.n, s.pairs, 1, s.n, s.n, st));
   RN_TRY(colsum(dZ, dV, s.G, s.B * s.n, 1, s.n, 0, 1, s.n, st));
-  RN_TRY(relation_layer0_bwd(s, x, q, g_w, dU, dV, delta, dx, dq, dg_w, dg_b, st));
+  RN_TRY(relation_layer0_bwd(s, x, q, g_w, dU, dV, delta, dx, dq, dg_w, dg_b, ws, splitk_floats(s), st));
   return RN_OK;
 }
 

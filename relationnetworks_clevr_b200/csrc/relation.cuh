@@ -36,9 +36,10 @@ int relation_pre(const RelShape& s, const float* x, const float* q, const float*
 
 // layer-0 backward shared by every precision mode: from dU [B,n,G], dV [B,n,G] to dx, dq (when
 // qinj == 0), dW0, db0.  `delta` [B,G] scratch.
+// `ws` / `ws_floats`: split-K workspace for the long-K products (dU^T X, dV^T X: K = B*n).
 int relation_layer0_bwd(const RelShape& s, const float* x, const float* q, const float* const* g_w, const float* dU,
                         const float* dV, float* delta, float* dx, float* dq, float* const* dg_w,
-                        float* const* dg_b, cudaStream_t st);
+                        float* const* dg_b, float* ws, size_t ws_floats, cudaStream_t st);
 
 // question-injection gradients at layer l == qinj > 0 from the per-sample column sums delta [B,G].
 int relation_qinj_bwd(const RelShape& s, int l, const float* q, const float* const* g_w, const float* delta,

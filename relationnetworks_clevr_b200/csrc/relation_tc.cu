@@ -842,7 +842,7 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
   dz1_reduce_kernel<<<dim3(s.B, kNKC), 256, 0, st>>>(reinterpret_cast<const char*>(ws.dZ), (size_t)4 * kATile, ws.dU,
                                                       ws.dV, ws.scale, s.n, tps);
   RN_LAUNCH_CHECK("dz1_reduce_kernel");
-  return relation_layer0_bwd(s, x, q, g_w, ws.dU, ws.dV, ws.delta, dx, dq, dg_w, dg_b, st);
+  return relation_layer0_bwd(s, x, q, g_w, ws.dU, ws.dV, ws.delta, dx, dq, dg_w, dg_b, ws.partial, (size_t)256 * kG * kG, st);
 }
 
 }  // namespace rn

