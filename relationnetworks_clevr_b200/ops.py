@@ -141,7 +141,6 @@ class RelationFunction(torch.autograd.Function):
             check(lib().rn_relation_bwd(C.byref(cfg), dxg_.data_ptr(), x_.data_ptr(), q_.data_ptr(), ptr_array(ws),
                                         ctx.saved_buf.data_ptr(), dx.data_ptr(), dq.data_ptr(), ptr_array(dws),
                                         ptr_array(dbs), scratch.data_ptr(), _stream()), "rn_relation_bwd")
-        ctx.saved_buf = None
         grads = []
         for dw, db in zip(dws, dbs):
             grads += [dw, db]
@@ -249,7 +248,6 @@ class ConvObjectsFunction(torch.autograd.Function):
         scratch = _scratch_bytes(img_.device, "conv", ctx.scratch_floats * 4)
         check(lib().rn_conv_bwd(C.byref(cfg), img_.data_ptr(), dobj.data_ptr(), layers, ctx.saved_buf.data_ptr(), garr,
                                 scratch.data_ptr(), _stream()), "rn_conv_bwd")
-        ctx.saved_buf = None
         return (None, None, None, None, None, *grads)
 
 
