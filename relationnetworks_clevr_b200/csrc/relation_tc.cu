@@ -31,12 +31,15 @@ constexpr int kATile = kAChunk * kNKC;        // 64 KB
 constexpr int kWChunk = kG * kKC * 2;         // 32 KB
 constexpr int kStages = 3;
 constexpr int kTcLayers = 3;            // g layers 1..3 run on the tensor cores
-constexpr int kFwdThreads = 384;
+constexpr int kSlotThreads = 256;       // 8 generation / epilogue warps per tile slot
+constexpr int kChainThreads = 128 + 2 * kSlotThreads;
 constexpr int kSmemA = 0;
 constexpr int kSmemW = 2 * kATile;
 constexpr int kSmemBar = kSmemW + kStages * kWChunk;
-constexpr int kSmemTotal = kSmemBar + 128;
-constexpr int kSmemLaunch = kSmemTotal + 1024;   // slack to align the carve-up to 1024 B (SWIZZLE_128B atoms)
+constexpr int kSmemBias = kSmemBar + 128;        // 2 slots x 256 floats: the current layer's bias
+constexpr int kSmemTotal = kSmemBias + 2 * kG * 4;
+constexpr int kSmemLaunch = 232448;              // the sm_100 per-block maximum
+constexpr int kSmemSlack = kSmemLaunch - kSmemTotal;   // room to align the carve-up to 1024 B (SWIZZLE_128B atoms)
 constexpr uint32_t kIdescFwd = idesc_f16(kTileM, kG, 0, 0);
 
 // byte offset of element (row, col) inside a [rows x 64] fp16 K-major SWIZZLE_128B chunk
@@ -139,16 +142,39 @@ __device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
   return x[0];
 }
 
+// fp32 pair -> packed fp16x2 with ReLU in the conversion (F2FP.RELU): lo -> low half, hi -> high half
+__device__ __forceinline__ uint32_t pack_relu_half2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// Sum x[0..15] over the 32 lanes (rows): afterwards lanes 2c and 2c+1 both hold the total of element c.
+__device__ __forceinline__ float warp_transpose_sum16(float (&x)[16], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 2; off >>= 1) {
+    const int h = off >> 1;                       // values kept after this step
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int e = 0; e < h; ++e) {
+      const float send = upper ? x[e] : x[e + h];
+      const float keep = upper ? x[e + h] : x[e];
+      x[e] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);
+}
+
 // Forward generation: H1 rows of one tile -> swizzled fp16 A operand (the pair matrix never exists anywhere).
-// Warp `q` (0..3) of the warpgroup owns rows [32q, 32q+32).  Lane mapping: 4 rows x 8 sixteen-byte groups per
-// step -> 256-byte coalesced reads of U, conflict-free STS.  M1 sign bits use the permuted layout
-// word j = (col % 64) / 8, bit = (col / 64) * 8 + col % 8.
+// 8 warps per slot: warp (q, half) owns rows [32q, 32q+32) x columns [128*half, 128*half+128).
+// Lane mapping: 4 rows x 8 sixteen-byte groups per step -> 256-byte coalesced reads of U, conflict-free STS.
+// M1 sign bits use the permuted layout  word j = (col % 64) / 8, bit = (col / 64) * 8 + col % 8.
 template <bool SAVE>
-__device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
+__device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char* a_tile, int q, int half, int lane) {
   const int b = tile / p.tiles_per_sample;
   const int p0 = (tile % p.tiles_per_sample) * kTileM;
-  const float* Ub = p.U + (size_t)b * p.n * kG;
-  const float* Vb = p.Vb + (size_t)b * p.n * kG;
+  const float* Ub = p.U + (size_t)b * p.n * kG + half * 128;
+  const float* Vb = p.Vb + (size_t)b * p.n * kG + half * 128;
   const int sub = lane >> 3, j = lane & 7;
 #pragma unroll 2
   for (int g = 0; g < 8; ++g) {
@@ -157,58 +183,58 @@ __device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char
     const int a = pr / p.n, c = pr - a * p.n;
     const float4* up = reinterpret_cast<const float4*>(Ub + (size_t)c * kG + j * 8);
     const float4* vp = reinterpret_cast<const float4*>(Vb + (size_t)a * kG + j * 8);
-    uint32_t bits = 0;
+    const float4 u0 = __ldg(up), u1 = __ldg(up + 1), u2 = __ldg(up + 16), u3 = __ldg(up + 17);
+    const float4 v0 = __ldg(vp), v1 = __ldg(vp + 1), v2 = __ldg(vp + 16), v3 = __ldg(vp + 17);
+    const float z[16] = {u0.x + v0.x, u0.y + v0.y, u0.z + v0.z, u0.w + v0.w, u1.x + v1.x, u1.y + v1.y, u1.z + v1.z, u1.w + v1.w,
+                         u2.x + v2.x, u2.y + v2.y, u2.z + v2.z, u2.w + v2.w, u3.x + v3.x, u3.y + v3.y, u3.z + v3.z, u3.w + v3.w};
 #pragma unroll
-    for (int kc = 0; kc < kNKC; ++kc) {
-      const float4 u0 = __ldg(up + kc * 16), u1 = __ldg(up + kc * 16 + 1);
-      const float4 v0 = __ldg(vp + kc * 16), v1 = __ldg(vp + kc * 16 + 1);
-      const float h[8] = {fmaxf(u0.x + v0.x, 0.f), fmaxf(u0.y + v0.y, 0.f), fmaxf(u0.z + v0.z, 0.f), fmaxf(u0.w + v0.w, 0.f),
-                          fmaxf(u1.x + v1.x, 0.f), fmaxf(u1.y + v1.y, 0.f), fmaxf(u1.z + v1.z, 0.f), fmaxf(u1.w + v1.w, 0.f)};
-      if (SAVE) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bits |= (h[e] > 0.f ? 1u : 0u) << (kc * 8 + e);
-      }
+    for (int kk = 0; kk < 2; ++kk) {
       uint4 o;
-      o.x = pack_half2(h[0], h[1]);
-      o.y = pack_half2(h[2], h[3]);
-      o.z = pack_half2(h[4], h[5]);
-      o.w = pack_half2(h[6], h[7]);
-      *reinterpret_cast<uint4*>(a_tile + kc * kAChunk + sw128_offset(row, j * 8)) = o;
+      o.x = pack_relu_half2(z[kk * 8 + 0], z[kk * 8 + 1]);
+      o.y = pack_relu_half2(z[kk * 8 + 2], z[kk * 8 + 3]);
+      o.z = pack_relu_half2(z[kk * 8 + 4], z[kk * 8 + 5]);
+      o.w = pack_relu_half2(z[kk * 8 + 6], z[kk * 8 + 7]);
+      *reinterpret_cast<uint4*>(a_tile + (half * 2 + kk) * kAChunk + sw128_offset(row, j * 8)) = o;
     }
-    if (SAVE) p.masks[((size_t)tile * kTileM + row) * 8 + j] = bits;      // masks[0] = M1
+    if (SAVE) {
+      uint32_t bits = 0;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) bits |= (z[e] > 0.f ? 1u : 0u) << e;
+      // masks[0] = M1: word j of the row, this warp's two K-chunks fill its low (half 0) or high (half 1) 16 bits
+      reinterpret_cast<uint16_t*>(p.masks)[(((size_t)tile * kTileM + row) * 8 + j) * 2 + half] = (uint16_t)bits;
+    }
   }
 }
 
 // Backward generation: dZ4[r, :] = S * dxg[b, :] where Z4[r, :] > 0 -> swizzled fp16 A operand, plus the
-// per-(tile, quarter) column sums of dZ4 (for db3).  Same lane mapping as generate_h1.
-__device__ __forceinline__ void generate_dz4(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
+// per-(tile, quarter) column sums of dZ4 (for db3).  Same warp / lane mapping as generate_h1.
+__device__ __forceinline__ void generate_dz4(const ChainParams& p, int tile, char* a_tile, int q, int half, int lane) {
   const int b = tile / p.tiles_per_sample;
   const int sub = lane >> 3, j = lane & 7;
   const float S = __ldg(p.scale);
-  float d[kNKC][8], acc[kNKC][8];
+  float d[16], acc[16];
+  {
+    const float4* dp = reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + half * 128 + j * 8);
+    const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 16), d3 = __ldg(dp + 17);
+    const float t[16] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w, d3.x, d3.y, d3.z, d3.w};
 #pragma unroll
-  for (int kc = 0; kc < kNKC; ++kc) {
-    const float4 d0 = __ldg(reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + kc * 64 + j * 8));
-    const float4 d1 = __ldg(reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + kc * 64 + j * 8 + 4));
-    d[kc][0] = d0.x * S; d[kc][1] = d0.y * S; d[kc][2] = d0.z * S; d[kc][3] = d0.w * S;
-    d[kc][4] = d1.x * S; d[kc][5] = d1.y * S; d[kc][6] = d1.z * S; d[kc][7] = d1.w * S;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[kc][e] = 0.f;
+    for (int e = 0; e < 16; ++e) { d[e] = t[e] * S; acc[e] = 0.f; }
   }
   const uint32_t* m4 = p.masks + ((size_t)3 * p.num_tiles + tile) * kTileM * 8;
 #pragma unroll 2
   for (int g = 0; g < 8; ++g) {
     const int row = q * 32 + g * 4 + sub;
-    // cols kc*64 + j*8 + e live in word kc*2 + (j >> 2), bits (j & 3)*8 + e
 #pragma unroll
-    for (int kc = 0; kc < kNKC; ++kc) {
+    for (int kk = 0; kk < 2; ++kk) {
+      const int kc = half * 2 + kk;
+      // cols kc*64 + j*8 + e live in word kc*2 + (j >> 2), bits (j & 3)*8 + e
       const uint32_t word = __ldg(m4 + (size_t)row * 8 + kc * 2 + (j >> 2));
       const uint32_t byte = (word >> ((j & 3) * 8)) & 0xffu;
       float h[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        h[e] = ((byte >> e) & 1u) ? d[kc][e] : 0.f;
-        acc[kc][e] += h[e];
+        h[e] = ((byte >> e) & 1u) ? d[kk * 8 + e] : 0.f;
+        acc[kk * 8 + e] += h[e];
       }
       uint4 o;
       o.x = pack_half2(h[0], h[1]);
@@ -218,24 +244,27 @@ __device__ __forceinline__ void generate_dz4(const ChainParams& p, int tile, cha
       *reinterpret_cast<uint4*>(a_tile + kc * kAChunk + sw128_offset(row, j * 8)) = o;
     }
   }
-  // reduce over the 4 sub-rows (lane bits 3 and 4); lanes with sub == 0 store 32 columns each
-  float* part = p.colpart + (((size_t)2 * p.num_tiles + tile) * 4 + q) * kG;
+  // reduce over the 4 sub-rows (lane bits 3 and 4); lanes with sub == 0 store their 16 columns
+  float* part = p.colpart + (((size_t)2 * p.num_tiles + tile) * 4 + q) * kG + half * 128;
 #pragma unroll
-  for (int kc = 0; kc < kNKC; ++kc)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = acc[kc][e];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (sub == 0) part[kc * 64 + j * 8 + e] = v;
-    }
+  for (int e = 0; e < 16; ++e) {
+    float v = acc[e];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (sub == 0) part[(e >> 3) * 64 + j * 8 + (e & 7)] = v;
+  }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainParams p) {
+__global__ void __launch_bounds__(kChainThreads, 1) rn_g_chain_kernel(const ChainParams p) {
   constexpr bool SAVE = MODE != kFwdEval;        // training forward and dgrad stream operand images to HBM
   extern __shared__ char smem_raw[];
-  char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  if (pad > kSmemSlack) {
+    if (threadIdx.x == 0) printf("rn_b200: dynamic smem base misaligned by %u bytes (slack %d)\n", pad, kSmemSlack);
+    __trap();
+  }
+  char* smem = smem_raw + pad;
   Bars* bars = reinterpret_cast<Bars*>(smem + kSmemBar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_tiles = tiles_of_cta(p.num_tiles);
@@ -246,7 +275,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
       mbar_init(smem_u32(&bars->w_empty[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bars->a_full[s]), 128);
+      mbar_init(smem_u32(&bars->a_full[s]), kSlotThreads);
       mbar_init(smem_u32(&bars->acc_full[s]), 1);
     }
     fence_mbar_init();
@@ -256,6 +285,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
+
+  // register re-distribution: the producer / issuer warpgroup needs few registers, the 16 epilogue warps many
+  // (launch allocation 96/thread = 61440; 128*56 + 512*104 = 60416)
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
 
   // job sequence shared by producer and issuer: for round r: for layer 0..2: for slot 0..1 (if its tile exists)
   if (warp == 0) {
@@ -314,150 +348,158 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
       }
     }
   } else if (warp >= 4) {
-    // ================= generation / epilogue warpgroups =================
-    const int s = (warp - 4) >> 2;             // tile slot
+    // ================= generation / epilogue warps: 8 per tile slot =================
+    const int s = (warp - 4) >> 3;             // tile slot
+    const int half = ((warp - 4) >> 2) & 1;    // column half [128*half, 128*half + 128)
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int wg_tid = threadIdx.x - 128 - s * 128;
+    const int slot_tid = threadIdx.x - 128 - s * kSlotThreads;
     char* a_tile = smem + kSmemA + s * kATile;
+    float* sbias = reinterpret_cast<float*>(smem + kSmemBias) + s * kG;
     const uint32_t a_full = smem_u32(&bars->a_full[s]);
     const uint32_t acc_full = smem_u32(&bars->acc_full[s]);
     const uint32_t bar_id = 1 + s;
     uint32_t acc_phase = 0;
+    auto slot_sync = [&]() { named_bar_sync(bar_id, kSlotThreads); };
 
     // stream the freshly written operand image of this slot to HBM (one elected thread, bulk async store)
     auto store_image = [&](char* dst) {
-      named_bar_sync(bar_id, 128);              // whole image written and fenced by every thread
-      if (wg_tid == 0) {
+      slot_sync();                              // whole image written and fenced by every thread
+      if (slot_tid == 0) {
         bulk_s2g(dst, smem_u32(a_tile), kATile);
         bulk_commit();
       }
     };
     // before overwriting the A buffer: the previous image store must have finished READING it
     auto wait_image_read = [&]() {
-      if (wg_tid == 0) bulk_wait_read0();
-      named_bar_sync(bar_id, 128);
+      if (slot_tid == 0) bulk_wait_read0();
+      slot_sync();
     };
 
     for (int i = s; i < my_tiles; i += 2) {
       const int tile = blockIdx.x + i * gridDim.x;
       const int b = tile / p.tiles_per_sample;
       if (SAVE) wait_image_read();
-      if (MODE == kDgrad) generate_dz4(p, tile, a_tile, q, lane);
-      else generate_h1<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
+      if (MODE == kDgrad) generate_dz4(p, tile, a_tile, q, half, lane);
+      else generate_h1<MODE == kFwdTrain>(p, tile, a_tile, q, half, lane);
       fence_proxy_async_smem();
       if (MODE == kFwdTrain) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile);
       if (MODE == kDgrad) store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + 3) * kATile);
       mbar_arrive(a_full);
 
       for (int layer = 0; layer < kTcLayers; ++layer) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * kG;
         if (MODE != kDgrad) {
           // ---------------- forward epilogue ----------------
-          const float* bias = p.bias[layer] + (size_t)b * p.bias_stride[layer];
-          uint32_t* mrow = SAVE ? p.masks + (((size_t)(layer + 1) * p.num_tiles + tile) * kTileM + row) * 8 : nullptr;
+          // stage this layer's bias (per-sample for the question-injection layer) in smem while the MMAs run
+          if (!SAVE) slot_sync();               // everyone is done reading the previous layer's bias
+          if (slot_tid < kG / 4)
+            reinterpret_cast<float4*>(sbias)[slot_tid] =
+                __ldg(reinterpret_cast<const float4*>(p.bias[layer] + (size_t)b * p.bias_stride[layer]) + slot_tid);
+          uint32_t* mrow = SAVE ? p.masks + (((size_t)(layer + 1) * p.num_tiles + tile) * kTileM + row) * 8 + half * 4 : nullptr;
           mbar_wait(acc_full, acc_phase);
           acc_phase ^= 1;
           tc_fence_after_sync();
-          if (layer < kTcLayers - 1) {
-            if (SAVE) wait_image_read();
-            uint32_t mw[8];
+          if (SAVE && layer < kTcLayers - 1) wait_image_read();   // also orders the bias staging
+          else slot_sync();
+          uint32_t mw[4] = {0u, 0u, 0u, 0u};
+          float* part = p.xg_part + ((size_t)tile * 4 + q) * kG;
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
-              uint32_t r[32];
-              tmem_ld32(taddr + cc * 32, r);
-              tmem_ld_wait();
-              uint32_t bits = 0;
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const int col0 = half * 128 + c8 * 16;
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + s * kG + col0, r);
+            tmem_ld_wait();
+            float z[16];
 #pragma unroll
-              for (int g4 = 0; g4 < 4; ++g4) {
-                float v[8];
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + g4 * 8));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + g4 * 8 + 4));
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  v[e] = fmaxf(__uint_as_float(r[g4 * 8 + e]) + bb[e], 0.f);
-                  bits |= (v[e] > 0.f ? 1u : 0u) << (g4 * 8 + e);
-                }
-                uint4 o;
-                o.x = pack_half2(v[0], v[1]);
-                o.y = pack_half2(v[2], v[3]);
-                o.z = pack_half2(v[4], v[5]);
-                o.w = pack_half2(v[6], v[7]);
-                const int col = cc * 32 + g4 * 8;
-                *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + sw128_offset(row, col & 63)) = o;
-              }
-              mw[cc] = bits;
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const float4 bv = *reinterpret_cast<const float4*>(sbias + col0 + g4 * 4);
+              z[g4 * 4 + 0] = __uint_as_float(r[g4 * 4 + 0]) + bv.x;
+              z[g4 * 4 + 1] = __uint_as_float(r[g4 * 4 + 1]) + bv.y;
+              z[g4 * 4 + 2] = __uint_as_float(r[g4 * 4 + 2]) + bv.z;
+              z[g4 * 4 + 3] = __uint_as_float(r[g4 * 4 + 3]) + bv.w;
             }
             if (SAVE) {
-              *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-              *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+              uint32_t bits = 0;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) bits |= (z[e] > 0.f ? 1u : 0u) << ((c8 & 1) * 16 + e);
+              mw[c8 >> 1] |= bits;
             }
+            if (layer < kTcLayers - 1) {
+#pragma unroll
+              for (int g8 = 0; g8 < 2; ++g8) {
+                uint4 o;
+                o.x = pack_relu_half2(z[g8 * 8 + 0], z[g8 * 8 + 1]);
+                o.y = pack_relu_half2(z[g8 * 8 + 2], z[g8 * 8 + 3]);
+                o.z = pack_relu_half2(z[g8 * 8 + 4], z[g8 * 8 + 5]);
+                o.w = pack_relu_half2(z[g8 * 8 + 6], z[g8 * 8 + 7]);
+                const int col = col0 + g8 * 8;
+                *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + sw128_offset(row, col & 63)) = o;
+              }
+            } else {
+              // last layer: ReLU + pair-sum.  Column sums over this warp's 32 rows by shuffle transpose-reduce.
+#pragma unroll
+              for (int e = 0; e < 16; ++e) z[e] = fmaxf(z[e], 0.f);
+              const float tot = warp_transpose_sum16(z, lane);        // lanes 2c, 2c+1 hold column col0 + c
+              if ((lane & 1) == 0) part[col0 + (lane >> 1)] = tot;
+            }
+          }
+          if (SAVE) *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+          if (layer < kTcLayers - 1) {
             fence_proxy_async_smem();
             if (SAVE) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + layer + 1) * kATile);
             tc_fence_before_sync();
             mbar_arrive(a_full);
           } else {
-            // last layer: ReLU + pair-sum.  Column sums over this warp's 32 rows by shuffle transpose-reduce.
-            float* part = p.xg_part + ((size_t)tile * 4 + q) * kG;
-            uint32_t mw[8];
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
-              uint32_t r[32];
-              tmem_ld32(taddr + cc * 32, r);
-              tmem_ld_wait();
-              float x[32];
-              uint32_t bits = 0;
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                x[e] = fmaxf(__uint_as_float(r[e]) + __ldg(bias + cc * 32 + e), 0.f);
-                bits |= (x[e] > 0.f ? 1u : 0u) << e;
-              }
-              mw[cc] = bits;
-              part[cc * 32 + lane] = warp_transpose_sum(x, lane);     // lane L holds the sum of column cc*32 + L
-            }
-            if (SAVE) {
-              *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-              *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
-            }
             tc_fence_before_sync();
           }
         } else {
           // ---------------- data-gradient epilogue: dZ_l = dH_l .* (Z_l > 0), l = 3 - layer ----------------
           const int l = kTcLayers - layer;                // 3, 2, 1
           const uint32_t* mrow = p.masks + (((size_t)(l - 1) * p.num_tiles + tile) * kTileM + row) * 8;
-          const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow));
-          const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow) + 1);
-          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          uint32_t mw[8];
+          if (l == 1) {                                   // permuted Z1 layout: all 8 words are needed
+            const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow));
+            const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow) + 1);
+            mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w; mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+          } else {
+            const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow) + half);
+            mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
+          }
           mbar_wait(acc_full, acc_phase);
           acc_phase ^= 1;
           tc_fence_after_sync();
           wait_image_read();
           float* part = l >= 2 ? p.colpart + (((size_t)(l - 2) * p.num_tiles + tile) * 4 + q) * kG : nullptr;
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            uint32_t r[32];
-            tmem_ld32(taddr + cc * 32, r);
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const int col0 = half * 128 + c8 * 16;
+            const int cc = col0 >> 5;                 // 32-column word index within the row
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + s * kG + col0, r);
             tmem_ld_wait();
-            float x[32];
+            float x[16];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              // Z2..Z4 masks: word cc, bit e.  Z1 mask (l == 1): permuted layout written by generate_h1.
-              const uint32_t bit = (l == 1) ? (mw[(cc & 1) * 4 + (e >> 3)] >> ((cc >> 1) * 8 + (e & 7))) & 1u
-                                            : (mw[cc] >> e) & 1u;
+            for (int e = 0; e < 16; ++e) {
+              const int e32 = (c8 & 1) * 16 + e;      // position inside the 32-column word
+              // Z2..Z4 masks: word cc, bit e32.  Z1 mask (l == 1): permuted layout written by generate_h1.
+              const uint32_t bit = (l == 1) ? (mw[(cc & 1) * 4 + (e32 >> 3)] >> ((cc >> 1) * 8 + (e32 & 7))) & 1u
+                                            : (mw[c8 >> 1] >> e32) & 1u;
               x[e] = bit ? __uint_as_float(r[e]) : 0.f;
             }
 #pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
+            for (int g8 = 0; g8 < 2; ++g8) {
               uint4 o;
-              o.x = pack_half2(x[g4 * 8 + 0], x[g4 * 8 + 1]);
-              o.y = pack_half2(x[g4 * 8 + 2], x[g4 * 8 + 3]);
-              o.z = pack_half2(x[g4 * 8 + 4], x[g4 * 8 + 5]);
-              o.w = pack_half2(x[g4 * 8 + 6], x[g4 * 8 + 7]);
-              const int col = cc * 32 + g4 * 8;
+              o.x = pack_half2(x[g8 * 8 + 0], x[g8 * 8 + 1]);
+              o.y = pack_half2(x[g8 * 8 + 2], x[g8 * 8 + 3]);
+              o.z = pack_half2(x[g8 * 8 + 4], x[g8 * 8 + 5]);
+              o.w = pack_half2(x[g8 * 8 + 6], x[g8 * 8 + 7]);
+              const int col = col0 + g8 * 8;
               *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + sw128_offset(row, col & 63)) = o;
             }
-            if (l >= 2) part[cc * 32 + lane] = warp_transpose_sum(x, lane);
+            if (l >= 2) {
+              const float tot = warp_transpose_sum16(x, lane);
+              if ((lane & 1) == 0) part[col0 + (lane >> 1)] = tot;
+            }
           }
           fence_proxy_async_smem();
           store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + (l - 1)) * kATile);
@@ -466,7 +508,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
         }
       }
     }
-    if (SAVE && wg_tid == 0) bulk_wait0();
+    if (SAVE && slot_tid == 0) bulk_wait0();
   }
 
   tc_fence_before_sync();
@@ -742,7 +784,7 @@ template <int MODE>
 static int launch_chain(const ChainParams& p, cudaStream_t st) {
   const int grid = std::min(p.num_tiles, sm_count());
   RN_CUDA(cudaFuncSetAttribute(rn_g_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
-  rn_g_chain_kernel<MODE><<<grid, kFwdThreads, kSmemLaunch, st>>>(p);
+  rn_g_chain_kernel<MODE><<<grid, kChainThreads, kSmemLaunch, st>>>(p);
   RN_LAUNCH_CHECK("rn_g_chain_kernel");
   return RN_OK;
 }
