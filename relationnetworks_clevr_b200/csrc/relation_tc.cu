@@ -17,6 +17,7 @@
 #include "tc_ptx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace rn {
 
@@ -31,16 +32,16 @@ constexpr int kATile = kAChunk * kNKC;        // 64 KB
 constexpr int kWChunk = kG * kKC * 2;         // 32 KB
 constexpr int kStages = 3;
 constexpr int kTcLayers = 3;            // g layers 1..3 run on the tensor cores
-constexpr int kSlotThreads = 256;       // 8 generation / epilogue warps per tile slot
-constexpr int kChainThreads = 128 + 2 * kSlotThreads;
+constexpr int kFwdThreads = 384;
 constexpr int kSmemA = 0;
 constexpr int kSmemW = 2 * kATile;
 constexpr int kSmemBar = kSmemW + kStages * kWChunk;
-constexpr int kSmemBias = kSmemBar + 128;        // 2 slots x 256 floats: the current layer's bias
-constexpr int kSmemTotal = kSmemBias + 2 * kG * 4;
-constexpr int kSmemLaunch = 232448;              // the sm_100 per-block maximum
-constexpr int kSmemSlack = kSmemLaunch - kSmemTotal;   // room to align the carve-up to 1024 B (SWIZZLE_128B atoms)
+constexpr int kSmemTotal = kSmemBar + 256;
+constexpr int kSmemLaunch = kSmemTotal + 1024;   // slack to align the carve-up to 1024 B (SWIZZLE_128B atoms)
 constexpr uint32_t kIdescFwd = idesc_f16(kTileM, kG, 0, 0);
+constexpr uint32_t kIdescFwd2 = idesc_f16(2 * kTileM, kG, 0, 0);   // CTA pair: M = 256
+constexpr int kStages2 = 6;                 // CTA-pair mode: each CTA stages only its N-half (16 KB) of a weight chunk
+constexpr int kWHalf = kWChunk / 2;
 
 // byte offset of element (row, col) inside a [rows x 64] fp16 K-major SWIZZLE_128B chunk
 __host__ __device__ inline uint32_t sw128_offset(int row, int col) {
@@ -112,12 +113,12 @@ struct ChainParams {
   const float* dxg;                // [B, 256]
   const float* scale;              // [0] = S (power of two applied to dxg), [1] = 1/S
   __half* dZ;                      // [tiles][4] x 64 KB images dZ1..dZ4 (scaled by S)
-  float* colpart;                  // [3][tiles][4][256] column sums of dZ2, dZ3, dZ4 per (tile, row quarter)
 };
 
 struct Bars {
-  uint64_t w_full[kStages];
-  uint64_t w_empty[kStages];
+  uint64_t w_full[kStages2];      // 1-CTA mode uses the first kStages entries
+  uint64_t w_empty[kStages2];
+  uint64_t peer_full[kStages2];   // CTA-pair mode, leader only: the peer CTA's half of the chunk has landed
   uint64_t a_full[2];
   uint64_t acc_full[2];
   uint32_t tmem_base;
@@ -142,39 +143,23 @@ __device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
   return x[0];
 }
 
-// fp32 pair -> packed fp16x2 with ReLU in the conversion (F2FP.RELU): lo -> low half, hi -> high half
+// fp32 pair -> packed fp16x2 with ReLU folded into the conversion (F2FP.RELU): lo -> low half, hi -> high half
 __device__ __forceinline__ uint32_t pack_relu_half2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 
-// Sum x[0..15] over the 32 lanes (rows): afterwards lanes 2c and 2c+1 both hold the total of element c.
-__device__ __forceinline__ float warp_transpose_sum16(float (&x)[16], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 2; off >>= 1) {
-    const int h = off >> 1;                       // values kept after this step
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int e = 0; e < h; ++e) {
-      const float send = upper ? x[e] : x[e + h];
-      const float keep = upper ? x[e + h] : x[e];
-      x[e] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);
-}
-
 // Forward generation: H1 rows of one tile -> swizzled fp16 A operand (the pair matrix never exists anywhere).
-// 8 warps per slot: warp (q, half) owns rows [32q, 32q+32) x columns [128*half, 128*half+128).
-// Lane mapping: 4 rows x 8 sixteen-byte groups per step -> 256-byte coalesced reads of U, conflict-free STS.
-// M1 sign bits use the permuted layout  word j = (col % 64) / 8, bit = (col / 64) * 8 + col % 8.
+// Warp `q` (0..3) of the warpgroup owns rows [32q, 32q+32).  Lane mapping: 4 rows x 8 sixteen-byte groups per
+// step -> 256-byte coalesced reads of U, conflict-free STS.  M1 sign bits use the permuted layout
+// word j = (col % 64) / 8, bit = (col / 64) * 8 + col % 8.
 template <bool SAVE>
-__device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char* a_tile, int q, int half, int lane) {
+__device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
   const int b = tile / p.tiles_per_sample;
   const int p0 = (tile % p.tiles_per_sample) * kTileM;
-  const float* Ub = p.U + (size_t)b * p.n * kG + half * 128;
-  const float* Vb = p.Vb + (size_t)b * p.n * kG + half * 128;
+  const float* Ub = p.U + (size_t)b * p.n * kG;
+  const float* Vb = p.Vb + (size_t)b * p.n * kG;
   const int sub = lane >> 3, j = lane & 7;
 #pragma unroll 2
   for (int g = 0; g < 8; ++g) {
@@ -183,59 +168,53 @@ __device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char
     const int a = pr / p.n, c = pr - a * p.n;
     const float4* up = reinterpret_cast<const float4*>(Ub + (size_t)c * kG + j * 8);
     const float4* vp = reinterpret_cast<const float4*>(Vb + (size_t)a * kG + j * 8);
-    const float4 u0 = __ldg(up), u1 = __ldg(up + 1), u2 = __ldg(up + 16), u3 = __ldg(up + 17);
-    const float4 v0 = __ldg(vp), v1 = __ldg(vp + 1), v2 = __ldg(vp + 16), v3 = __ldg(vp + 17);
-    const float z[16] = {u0.x + v0.x, u0.y + v0.y, u0.z + v0.z, u0.w + v0.w, u1.x + v1.x, u1.y + v1.y, u1.z + v1.z, u1.w + v1.w,
-                         u2.x + v2.x, u2.y + v2.y, u2.z + v2.z, u2.w + v2.w, u3.x + v3.x, u3.y + v3.y, u3.z + v3.z, u3.w + v3.w};
+    uint32_t bits = 0;
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
+    for (int kc = 0; kc < kNKC; ++kc) {
+      const float4 u0 = __ldg(up + kc * 16), u1 = __ldg(up + kc * 16 + 1);
+      const float4 v0 = __ldg(vp + kc * 16), v1 = __ldg(vp + kc * 16 + 1);
+      const float h[8] = {u0.x + v0.x, u0.y + v0.y, u0.z + v0.z, u0.w + v0.w, u1.x + v1.x, u1.y + v1.y, u1.z + v1.z, u1.w + v1.w};
+      if (SAVE) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bits |= (h[e] > 0.f ? 1u : 0u) << (kc * 8 + e);
+      }
       uint4 o;
-      o.x = pack_relu_half2(z[kk * 8 + 0], z[kk * 8 + 1]);
-      o.y = pack_relu_half2(z[kk * 8 + 2], z[kk * 8 + 3]);
-      o.z = pack_relu_half2(z[kk * 8 + 4], z[kk * 8 + 5]);
-      o.w = pack_relu_half2(z[kk * 8 + 6], z[kk * 8 + 7]);
-      *reinterpret_cast<uint4*>(a_tile + (half * 2 + kk) * kAChunk + sw128_offset(row, j * 8)) = o;
+      o.x = pack_relu_half2(h[0], h[1]);
+      o.y = pack_relu_half2(h[2], h[3]);
+      o.z = pack_relu_half2(h[4], h[5]);
+      o.w = pack_relu_half2(h[6], h[7]);
+      *reinterpret_cast<uint4*>(a_tile + kc * kAChunk + sw128_offset(row, j * 8)) = o;
     }
-    if (SAVE) {
-      uint32_t bits = 0;
-#pragma unroll
-      for (int e = 0; e < 16; ++e) bits |= (z[e] > 0.f ? 1u : 0u) << e;
-      // masks[0] = M1: word j of the row, this warp's two K-chunks fill its low (half 0) or high (half 1) 16 bits
-      reinterpret_cast<uint16_t*>(p.masks)[(((size_t)tile * kTileM + row) * 8 + j) * 2 + half] = (uint16_t)bits;
-    }
+    if (SAVE) p.masks[((size_t)tile * kTileM + row) * 8 + j] = bits;      // masks[0] = M1
   }
 }
 
-// Backward generation: dZ4[r, :] = S * dxg[b, :] where Z4[r, :] > 0 -> swizzled fp16 A operand, plus the
-// per-(tile, quarter) column sums of dZ4 (for db3).  Same warp / lane mapping as generate_h1.
-__device__ __forceinline__ void generate_dz4(const ChainParams& p, int tile, char* a_tile, int q, int half, int lane) {
+// Backward generation: dZ4[r, :] = S * dxg[b, :] where Z4[r, :] > 0 -> swizzled fp16 A operand.
+// Same lane mapping as generate_h1.  (Column sums of the dZ images are taken by the weight-gradient kernel.)
+__device__ __forceinline__ void generate_dz4(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
   const int b = tile / p.tiles_per_sample;
   const int sub = lane >> 3, j = lane & 7;
   const float S = __ldg(p.scale);
-  float d[16], acc[16];
-  {
-    const float4* dp = reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + half * 128 + j * 8);
-    const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 16), d3 = __ldg(dp + 17);
-    const float t[16] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w, d3.x, d3.y, d3.z, d3.w};
+  float d[kNKC][8];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) { d[e] = t[e] * S; acc[e] = 0.f; }
+  for (int kc = 0; kc < kNKC; ++kc) {
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + kc * 64 + j * 8));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + kc * 64 + j * 8 + 4));
+    d[kc][0] = d0.x * S; d[kc][1] = d0.y * S; d[kc][2] = d0.z * S; d[kc][3] = d0.w * S;
+    d[kc][4] = d1.x * S; d[kc][5] = d1.y * S; d[kc][6] = d1.z * S; d[kc][7] = d1.w * S;
   }
   const uint32_t* m4 = p.masks + ((size_t)3 * p.num_tiles + tile) * kTileM * 8;
 #pragma unroll 2
   for (int g = 0; g < 8; ++g) {
     const int row = q * 32 + g * 4 + sub;
+    // cols kc*64 + j*8 + e live in word kc*2 + (j >> 2), bits (j & 3)*8 + e
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      const int kc = half * 2 + kk;
-      // cols kc*64 + j*8 + e live in word kc*2 + (j >> 2), bits (j & 3)*8 + e
+    for (int kc = 0; kc < kNKC; ++kc) {
       const uint32_t word = __ldg(m4 + (size_t)row * 8 + kc * 2 + (j >> 2));
       const uint32_t byte = (word >> ((j & 3) * 8)) & 0xffu;
       float h[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        h[e] = ((byte >> e) & 1u) ? d[kk * 8 + e] : 0.f;
-        acc[kk * 8 + e] += h[e];
-      }
+      for (int e = 0; e < 8; ++e) h[e] = ((byte >> e) & 1u) ? d[kc][e] : 0.f;
       uint4 o;
       o.x = pack_half2(h[0], h[1]);
       o.y = pack_half2(h[2], h[3]);
@@ -244,52 +223,49 @@ __device__ __forceinline__ void generate_dz4(const ChainParams& p, int tile, cha
       *reinterpret_cast<uint4*>(a_tile + kc * kAChunk + sw128_offset(row, j * 8)) = o;
     }
   }
-  // reduce over the 4 sub-rows (lane bits 3 and 4); lanes with sub == 0 store their 16 columns
-  float* part = p.colpart + (((size_t)2 * p.num_tiles + tile) * 4 + q) * kG + half * 128;
-#pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    float v = acc[e];
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 16);
-    if (sub == 0) part[(e >> 3) * 64 + j * 8 + (e & 7)] = v;
-  }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kChainThreads, 1) rn_g_chain_kernel(const ChainParams p) {
+// CTA2 = true: the kernel runs as clusters of two CTAs on one TPC (cta_group::2).  Each CTA keeps its own tile
+// slots, A buffers, epilogue warps and TMEM accumulators, but ONE tcgen05.mma (M = 256) issued by the leader CTA
+// drives both tiles, and each CTA stages only its N-half of every weight chunk: half the L2->smem weight traffic
+// and half the shared-memory operand reads per SM -- the 1-CTA form is shared-memory-bandwidth bound.
+template <int MODE, bool CTA2>
+__global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainParams p) {
   constexpr bool SAVE = MODE != kFwdEval;        // training forward and dgrad stream operand images to HBM
+  constexpr int NST = CTA2 ? kStages2 : kStages;
+  constexpr int STAGE_BYTES = CTA2 ? kWHalf : kWChunk;
   extern __shared__ char smem_raw[];
-  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
-  if (pad > kSmemSlack) {
-    if (threadIdx.x == 0) printf("rn_b200: dynamic smem base misaligned by %u bytes (slack %d)\n", pad, kSmemSlack);
-    __trap();
-  }
-  char* smem = smem_raw + pad;
+  char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars* bars = reinterpret_cast<Bars*>(smem + kSmemBar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int my_tiles = tiles_of_cta(p.num_tiles);
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  // tiles of this CTA: 1-CTA: blockIdx, +grid, ...   CTA pair c of nc: tiles 2*(c + i*nc) + rank
+  const int tile_first = CTA2 ? 2 * (int)(blockIdx.x >> 1) + (int)rank : (int)blockIdx.x;
+  const int tile_step = CTA2 ? (int)gridDim.x : (int)gridDim.x;
+  const int my_tiles = CTA2 ? (p.num_tiles / 2 - (int)(blockIdx.x >> 1) + (int)(gridDim.x >> 1) - 1) / (int)(gridDim.x >> 1)
+                            : tiles_of_cta(p.num_tiles);
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(smem_u32(&bars->w_full[s]), 1);
       mbar_init(smem_u32(&bars->w_empty[s]), 1);
+      mbar_init(smem_u32(&bars->peer_full[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bars->a_full[s]), kSlotThreads);
+      mbar_init(smem_u32(&bars->a_full[s]), CTA2 ? 256 : 128);     // pair mode: both CTAs' warpgroups arrive at the leader
       mbar_init(smem_u32(&bars->acc_full[s]), 1);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  if (warp == 2) {
+    if (CTA2) tmem_alloc2(smem_u32(&bars->tmem_base), 512);
+    else tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  }
   tc_fence_before_sync();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();        // barriers of both CTAs initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
-
-  // register re-distribution: the producer / issuer warpgroup needs few registers, the 16 epilogue warps many
-  // (launch allocation 96/thread = 61440; 128*56 + 512*104 = 60416)
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
 
   // job sequence shared by producer and issuer: for round r: for layer 0..2: for slot 0..1 (if its tile exists)
   if (warp == 0) {
@@ -305,24 +281,27 @@ __global__ void __launch_bounds__(kChainThreads, 1) rn_g_chain_kernel(const Chai
               for (int kc = 0; kc < kNKC; ++kc) {
                 mbar_wait(smem_u32(&bars->w_empty[stage]), phase ^ 1);
                 const uint32_t full = smem_u32(&bars->w_full[stage]);
-                mbar_expect_tx(full, kWChunk);
-                const char* src = reinterpret_cast<const char*>(p.wpack) + ((size_t)(img_layer * 2 + pass) * kNKC + kc) * kWChunk;
-                bulk_g2s(smem_u32(smem + kSmemW + stage * kWChunk), src, kWChunk, full);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                mbar_expect_tx(full, STAGE_BYTES);
+                // pair mode: this CTA's N-half = rows [128*rank, 128*rank + 128) = the rank-th 16 KB of the chunk image
+                const char* src = reinterpret_cast<const char*>(p.wpack) + ((size_t)(img_layer * 2 + pass) * kNKC + kc) * kWChunk +
+                                  (CTA2 ? rank * kWHalf : 0);
+                bulk_g2s(smem_u32(smem + kSmemW + stage * STAGE_BYTES), src, STAGE_BYTES, full);
+                if (++stage == NST) { stage = 0; phase ^= 1; }
               }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
+    if (lane == 0 && (!CTA2 || rank == 0)) {
+      // ================= MMA issuer (pair mode: leader CTA only) =================
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
       for (int r = 0; 2 * r < my_tiles; ++r) {
         const int nslots = (2 * r + 1 < my_tiles) ? 2 : 1;
         for (int layer = 0; layer < kTcLayers; ++layer)
           for (int s = 0; s < nslots; ++s) {
-            mbar_wait(smem_u32(&bars->a_full[s]), a_phase[s]);
+            if (CTA2) mbar_wait_cluster(smem_u32(&bars->a_full[s]), a_phase[s]);
+            else mbar_wait(smem_u32(&bars->a_full[s]), a_phase[s]);
             a_phase[s] ^= 1;
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + s * kG;
@@ -331,189 +310,201 @@ __global__ void __launch_bounds__(kChainThreads, 1) rn_g_chain_kernel(const Chai
             for (int pass = 0; pass < p.passes; ++pass)
               for (int kc = 0; kc < kNKC; ++kc) {
                 mbar_wait(smem_u32(&bars->w_full[stage]), phase);
+                if (CTA2) mbar_wait_cluster(smem_u32(&bars->peer_full[stage]), phase);
                 tc_fence_after_sync();
-                const uint32_t b_base = smem_u32(smem + kSmemW + stage * kWChunk);
+                const uint32_t b_base = smem_u32(smem + kSmemW + stage * STAGE_BYTES);
 #pragma unroll
                 for (int k = 0; k < kKC / 16; ++k) {
                   const uint64_t ad = smem_desc_sw128(a_base + kc * kAChunk + k * 32, 16, 1024);
                   const uint64_t bd = smem_desc_sw128(b_base + k * 32, 16, 1024);
-                  mma_f16_ss(d_tmem, ad, bd, kIdescFwd, accumulate);
+                  if (CTA2) mma_f16_ss_2cta(d_tmem, ad, bd, kIdescFwd2, accumulate);
+                  else mma_f16_ss(d_tmem, ad, bd, kIdescFwd, accumulate);
                   accumulate = 1;
                 }
-                mma_commit(smem_u32(&bars->w_empty[stage]));      // ring stage free once these MMAs retire
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                // ring stage free (in both CTAs) once these MMAs retire
+                if (CTA2) mma_commit_2cta(smem_u32(&bars->w_empty[stage]), 3);
+                else mma_commit(smem_u32(&bars->w_empty[stage]));
+                if (++stage == NST) { stage = 0; phase ^= 1; }
               }
-            mma_commit(smem_u32(&bars->acc_full[s]));             // accumulator of (slot, layer) complete
+            // accumulator of (slot, layer) complete (in both CTAs)
+            if (CTA2) mma_commit_2cta(smem_u32(&bars->acc_full[s]), 3);
+            else mma_commit(smem_u32(&bars->acc_full[s]));
           }
+      }
+    } else if (CTA2 && lane == 0) {
+      // ================= peer CTA relay: tell the leader when this CTA's half of each chunk has landed =================
+      uint32_t stage = 0, phase = 0;
+      for (int r = 0; 2 * r < my_tiles; ++r) {
+        const int nslots = (2 * r + 1 < my_tiles) ? 2 : 1;
+        for (int job = 0; job < kTcLayers * nslots * p.passes * kNKC; ++job) {
+          mbar_wait(smem_u32(&bars->w_full[stage]), phase);
+          mbar_arrive_cluster(mapa_u32(smem_u32(&bars->peer_full[stage]), 0));
+          if (++stage == NST) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp >= 4) {
-    // ================= generation / epilogue warps: 8 per tile slot =================
-    const int s = (warp - 4) >> 3;             // tile slot
-    const int half = ((warp - 4) >> 2) & 1;    // column half [128*half, 128*half + 128)
+    // ================= generation / epilogue warpgroups =================
+    const int s = (warp - 4) >> 2;             // tile slot
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int slot_tid = threadIdx.x - 128 - s * kSlotThreads;
+    const int wg_tid = threadIdx.x - 128 - s * 128;
     char* a_tile = smem + kSmemA + s * kATile;
-    float* sbias = reinterpret_cast<float*>(smem + kSmemBias) + s * kG;
-    const uint32_t a_full = smem_u32(&bars->a_full[s]);
+    // pair mode: the A-operand-ready barrier lives in the leader CTA (it issues the MMAs for both tiles)
+    const uint32_t a_full = CTA2 ? mapa_u32(smem_u32(&bars->a_full[s]), 0) : smem_u32(&bars->a_full[s]);
     const uint32_t acc_full = smem_u32(&bars->acc_full[s]);
     const uint32_t bar_id = 1 + s;
     uint32_t acc_phase = 0;
-    auto slot_sync = [&]() { named_bar_sync(bar_id, kSlotThreads); };
 
     // stream the freshly written operand image of this slot to HBM (one elected thread, bulk async store)
     auto store_image = [&](char* dst) {
-      slot_sync();                              // whole image written and fenced by every thread
-      if (slot_tid == 0) {
+      named_bar_sync(bar_id, 128);              // whole image written and fenced by every thread
+      if (wg_tid == 0) {
         bulk_s2g(dst, smem_u32(a_tile), kATile);
         bulk_commit();
       }
     };
     // before overwriting the A buffer: the previous image store must have finished READING it
     auto wait_image_read = [&]() {
-      if (slot_tid == 0) bulk_wait_read0();
-      slot_sync();
+      if (wg_tid == 0) bulk_wait_read0();
+      named_bar_sync(bar_id, 128);
     };
 
     for (int i = s; i < my_tiles; i += 2) {
-      const int tile = blockIdx.x + i * gridDim.x;
+      const int tile = tile_first + i * tile_step;
       const int b = tile / p.tiles_per_sample;
       if (SAVE) wait_image_read();
-      if (MODE == kDgrad) generate_dz4(p, tile, a_tile, q, half, lane);
-      else generate_h1<MODE == kFwdTrain>(p, tile, a_tile, q, half, lane);
+      if (MODE == kDgrad) generate_dz4(p, tile, a_tile, q, lane);
+      else generate_h1<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
       fence_proxy_async_smem();
       if (MODE == kFwdTrain) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile);
       if (MODE == kDgrad) store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + 3) * kATile);
-      mbar_arrive(a_full);
+      if (CTA2) mbar_arrive_cluster(a_full); else mbar_arrive(a_full);
 
       for (int layer = 0; layer < kTcLayers; ++layer) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * kG;
         if (MODE != kDgrad) {
           // ---------------- forward epilogue ----------------
-          // stage this layer's bias (per-sample for the question-injection layer) in smem while the MMAs run
-          if (!SAVE) slot_sync();               // everyone is done reading the previous layer's bias
-          if (slot_tid < kG / 4)
-            reinterpret_cast<float4*>(sbias)[slot_tid] =
-                __ldg(reinterpret_cast<const float4*>(p.bias[layer] + (size_t)b * p.bias_stride[layer]) + slot_tid);
-          uint32_t* mrow = SAVE ? p.masks + (((size_t)(layer + 1) * p.num_tiles + tile) * kTileM + row) * 8 + half * 4 : nullptr;
+          const float* bias = p.bias[layer] + (size_t)b * p.bias_stride[layer];
+          uint32_t* mrow = SAVE ? p.masks + (((size_t)(layer + 1) * p.num_tiles + tile) * kTileM + row) * 8 : nullptr;
           mbar_wait(acc_full, acc_phase);
           acc_phase ^= 1;
           tc_fence_after_sync();
-          if (SAVE && layer < kTcLayers - 1) wait_image_read();   // also orders the bias staging
-          else slot_sync();
-          uint32_t mw[4] = {0u, 0u, 0u, 0u};
-          float* part = p.xg_part + ((size_t)tile * 4 + q) * kG;
+          if (layer < kTcLayers - 1) {
+            if (SAVE) wait_image_read();
+            uint32_t mw[8];
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            const int col0 = half * 128 + c8 * 16;
-            uint32_t r[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + s * kG + col0, r);
-            tmem_ld_wait();
-            float z[16];
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              const float4 bv = *reinterpret_cast<const float4*>(sbias + col0 + g4 * 4);
-              z[g4 * 4 + 0] = __uint_as_float(r[g4 * 4 + 0]) + bv.x;
-              z[g4 * 4 + 1] = __uint_as_float(r[g4 * 4 + 1]) + bv.y;
-              z[g4 * 4 + 2] = __uint_as_float(r[g4 * 4 + 2]) + bv.z;
-              z[g4 * 4 + 3] = __uint_as_float(r[g4 * 4 + 3]) + bv.w;
-            }
-            if (SAVE) {
+            for (int cc = 0; cc < 8; ++cc) {
+              uint32_t r[32];
+              tmem_ld32(taddr + cc * 32, r);
+              tmem_ld_wait();
               uint32_t bits = 0;
 #pragma unroll
-              for (int e = 0; e < 16; ++e) bits |= (z[e] > 0.f ? 1u : 0u) << ((c8 & 1) * 16 + e);
-              mw[c8 >> 1] |= bits;
-            }
-            if (layer < kTcLayers - 1) {
+              for (int g4 = 0; g4 < 4; ++g4) {
+                float v[8];
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + g4 * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + g4 * 8 + 4));
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int g8 = 0; g8 < 2; ++g8) {
+                for (int e = 0; e < 8; ++e) {
+                  v[e] = __uint_as_float(r[g4 * 8 + e]) + bb[e];
+                  bits |= (v[e] > 0.f ? 1u : 0u) << (g4 * 8 + e);
+                }
                 uint4 o;
-                o.x = pack_relu_half2(z[g8 * 8 + 0], z[g8 * 8 + 1]);
-                o.y = pack_relu_half2(z[g8 * 8 + 2], z[g8 * 8 + 3]);
-                o.z = pack_relu_half2(z[g8 * 8 + 4], z[g8 * 8 + 5]);
-                o.w = pack_relu_half2(z[g8 * 8 + 6], z[g8 * 8 + 7]);
-                const int col = col0 + g8 * 8;
+                o.x = pack_relu_half2(v[0], v[1]);
+                o.y = pack_relu_half2(v[2], v[3]);
+                o.z = pack_relu_half2(v[4], v[5]);
+                o.w = pack_relu_half2(v[6], v[7]);
+                const int col = cc * 32 + g4 * 8;
                 *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + sw128_offset(row, col & 63)) = o;
               }
-            } else {
-              // last layer: ReLU + pair-sum.  Column sums over this warp's 32 rows by shuffle transpose-reduce.
-#pragma unroll
-              for (int e = 0; e < 16; ++e) z[e] = fmaxf(z[e], 0.f);
-              const float tot = warp_transpose_sum16(z, lane);        // lanes 2c, 2c+1 hold column col0 + c
-              if ((lane & 1) == 0) part[col0 + (lane >> 1)] = tot;
+              mw[cc] = bits;
             }
-          }
-          if (SAVE) *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-          if (layer < kTcLayers - 1) {
+            if (SAVE) {
+              *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+              *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+            }
             fence_proxy_async_smem();
             if (SAVE) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + layer + 1) * kATile);
             tc_fence_before_sync();
-            mbar_arrive(a_full);
+            if (CTA2) mbar_arrive_cluster(a_full); else mbar_arrive(a_full);
           } else {
+            // last layer: ReLU + pair-sum.  Column sums over this warp's 32 rows by shuffle transpose-reduce.
+            float* part = p.xg_part + ((size_t)tile * 4 + q) * kG;
+            uint32_t mw[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              uint32_t r[32];
+              tmem_ld32(taddr + cc * 32, r);
+              tmem_ld_wait();
+              float x[32];
+              uint32_t bits = 0;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                x[e] = fmaxf(__uint_as_float(r[e]) + __ldg(bias + cc * 32 + e), 0.f);
+                bits |= (x[e] > 0.f ? 1u : 0u) << e;
+              }
+              mw[cc] = bits;
+              part[cc * 32 + lane] = warp_transpose_sum(x, lane);     // lane L holds the sum of column cc*32 + L
+            }
+            if (SAVE) {
+              *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+              *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+            }
             tc_fence_before_sync();
           }
         } else {
           // ---------------- data-gradient epilogue: dZ_l = dH_l .* (Z_l > 0), l = 3 - layer ----------------
           const int l = kTcLayers - layer;                // 3, 2, 1
           const uint32_t* mrow = p.masks + (((size_t)(l - 1) * p.num_tiles + tile) * kTileM + row) * 8;
-          uint32_t mw[8];
-          if (l == 1) {                                   // permuted Z1 layout: all 8 words are needed
-            const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow));
-            const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow) + 1);
-            mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w; mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
-          } else {
-            const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow) + half);
-            mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
-          }
+          const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow));
+          const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow) + 1);
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
           mbar_wait(acc_full, acc_phase);
           acc_phase ^= 1;
           tc_fence_after_sync();
           wait_image_read();
-          float* part = l >= 2 ? p.colpart + (((size_t)(l - 2) * p.num_tiles + tile) * 4 + q) * kG : nullptr;
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            const int col0 = half * 128 + c8 * 16;
-            const int cc = col0 >> 5;                 // 32-column word index within the row
-            uint32_t r[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + s * kG + col0, r);
+          for (int cc = 0; cc < 8; ++cc) {
+            uint32_t r[32];
+            tmem_ld32(taddr + cc * 32, r);
             tmem_ld_wait();
-            float x[16];
+            float x[32];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int e32 = (c8 & 1) * 16 + e;      // position inside the 32-column word
-              // Z2..Z4 masks: word cc, bit e32.  Z1 mask (l == 1): permuted layout written by generate_h1.
-              const uint32_t bit = (l == 1) ? (mw[(cc & 1) * 4 + (e32 >> 3)] >> ((cc >> 1) * 8 + (e32 & 7))) & 1u
-                                            : (mw[c8 >> 1] >> e32) & 1u;
+            for (int e = 0; e < 32; ++e) {
+              // Z2..Z4 masks: word cc, bit e.  Z1 mask (l == 1): permuted layout written by generate_h1.
+              const uint32_t bit = (l == 1) ? (mw[(cc & 1) * 4 + (e >> 3)] >> ((cc >> 1) * 8 + (e & 7))) & 1u
+                                            : (mw[cc] >> e) & 1u;
               x[e] = bit ? __uint_as_float(r[e]) : 0.f;
             }
 #pragma unroll
-            for (int g8 = 0; g8 < 2; ++g8) {
+            for (int g4 = 0; g4 < 4; ++g4) {
               uint4 o;
-              o.x = pack_half2(x[g8 * 8 + 0], x[g8 * 8 + 1]);
-              o.y = pack_half2(x[g8 * 8 + 2], x[g8 * 8 + 3]);
-              o.z = pack_half2(x[g8 * 8 + 4], x[g8 * 8 + 5]);
-              o.w = pack_half2(x[g8 * 8 + 6], x[g8 * 8 + 7]);
-              const int col = col0 + g8 * 8;
+              o.x = pack_half2(x[g4 * 8 + 0], x[g4 * 8 + 1]);
+              o.y = pack_half2(x[g4 * 8 + 2], x[g4 * 8 + 3]);
+              o.z = pack_half2(x[g4 * 8 + 4], x[g4 * 8 + 5]);
+              o.w = pack_half2(x[g4 * 8 + 6], x[g4 * 8 + 7]);
+              const int col = cc * 32 + g4 * 8;
               *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + sw128_offset(row, col & 63)) = o;
-            }
-            if (l >= 2) {
-              const float tot = warp_transpose_sum16(x, lane);
-              if ((lane & 1) == 0) part[col0 + (lane >> 1)] = tot;
             }
           }
           fence_proxy_async_smem();
           store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + (l - 1)) * kATile);
           tc_fence_before_sync();
-          if (layer < kTcLayers - 1) mbar_arrive(a_full);
+          if (layer < kTcLayers - 1) if (CTA2) mbar_arrive_cluster(a_full); else mbar_arrive(a_full);
         }
       }
     }
-    if (SAVE && slot_tid == 0) bulk_wait0();
+    if (SAVE && wg_tid == 0) bulk_wait0();
   }
 
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (CTA2) cluster_sync_all();        // the peer must not exit (or free TMEM) while the pair's MMAs may touch it
+  else __syncthreads();
+  if (warp == 2) {
+    if (CTA2) tmem_dealloc2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -537,6 +528,7 @@ struct WgradParams {
   const char* H;
   size_t h_stride;
   float* partial;          // [grid][256][256]
+  float* colpart;          // [tiles][256]: column sums of each dZ tile (bias / question-injection gradients)
   int num_tiles;
 };
 
@@ -557,7 +549,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradPa
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kWgStages; ++s) {
       mbar_init(smem_u32(&bars->full[s]), 1);
-      mbar_init(smem_u32(&bars->empty[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), 1 + 4);      // MMA commit + the 4 column-sum warps
     }
     mbar_init(smem_u32(&bars->done), 1);
     fence_mbar_init();
@@ -611,7 +603,36 @@ __global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradPa
       mma_commit(smem_u32(&bars->done));
     }
   } else {
-    // warps 2..5 -> TMEM lane quarters 2, 3, 0, 1
+    // warps 2..5.  Main loop: column sums of every dZ half-tile straight from the staged operand (these warps
+    // would otherwise idle; the tensor pipe is HBM-bound here) -> colpart[tile][256].  Thread t owns columns 2t, 2t+1.
+    {
+      const int t = threadIdx.x - 64;                  // 0..127
+      const int col = 2 * t;
+      const uint32_t coff = (uint32_t)(col >> 6) * 8192u + (uint32_t)(col & 7) * 2u;
+      const uint32_t grp = (uint32_t)((col & 63) >> 3);
+      uint32_t stage = 0, phase = 0;
+      float2 acc = make_float2(0.f, 0.f);
+      for (int i = 0; i < 2 * my_tiles; ++i) {
+        mbar_wait(smem_u32(&bars->full[stage]), phase);
+        const char* st = smem + stage * kWgStageBytes + coff;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+          const __half2 h = *reinterpret_cast<const __half2*>(st + (r >> 3) * 1024 + (r & 7) * 128 + ((grp ^ (uint32_t)(r & 7)) << 4));
+          const float2 f = __half22float2(h);
+          acc.x += f.x;
+          acc.y += f.y;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->empty[stage]));
+        if (i & 1) {                                   // second half of the tile
+          const size_t tile = blockIdx.x + (size_t)(i >> 1) * gridDim.x;
+          *reinterpret_cast<float2*>(p.colpart + tile * kG + col) = acc;
+          acc = make_float2(0.f, 0.f);
+        }
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    // final epilogue: TMEM lane quarters 2, 3, 0, 1
     const int q = warp & 3;
     mbar_wait(smem_u32(&bars->done), 0);
     tc_fence_after_sync();
@@ -741,7 +762,7 @@ struct TcBwdScratch {
   float* scale;
   __half* wpackT;
   __half* dZ;          // [tiles][4] x 64 KB
-  float* colpart;      // [3][tiles][4][256]
+  float* colpart;      // [3][tiles][256] (written by the weight-gradient kernels)
   float* partial;      // [grid][256][256]
   float* delta;        // [3][B][256]
   float* dU;
@@ -755,7 +776,7 @@ static TcBwdScratch tc_carve_bwd(const RelShape& s, void* scratch) {
   o.scale = c.take<float>(64);
   o.wpackT = reinterpret_cast<__half*>(c.take<char>(wpack_bytes()));
   o.dZ = reinterpret_cast<__half*>(c.take<char>(tiles * 4 * kATile));
-  o.colpart = c.take<float>(tiles * 3 * 4 * kG);
+  o.colpart = c.take<float>(tiles * 3 * kG);
   o.partial = c.take<float>((size_t)256 * kG * kG);
   o.delta = c.take<float>((size_t)3 * s.B * kG);
   o.dU = c.take<float>((size_t)s.B * s.n * kG);
@@ -767,7 +788,7 @@ size_t tc_scratch_bytes(const RelShape& s, bool training) {
   const size_t tiles = s.rows / kTileM;
   const size_t fwd = round_up(tiles * 4 * kG * 4, 256);
   if (!training) return fwd;
-  size_t bwd = 256 + round_up(wpack_bytes(), 256) + round_up(tiles * 4 * kATile, 256) + round_up(tiles * 3 * 4 * kG * 4, 256) +
+  size_t bwd = 256 + round_up(wpack_bytes(), 256) + round_up(tiles * 4 * kATile, 256) + round_up(tiles * 3 * kG * 4, 256) +
                round_up((size_t)256 * kG * kG * 4, 256) + round_up((size_t)3 * s.B * kG * 4, 256) +
                2 * round_up((size_t)s.B * s.n * kG * 4, 256);
   return fwd > bwd ? fwd : bwd;
@@ -782,9 +803,31 @@ static void fill_pack_args(const RelShape& s, const float* const* g_w, PackArgs&
 
 template <int MODE>
 static int launch_chain(const ChainParams& p, cudaStream_t st) {
+  // CTA-pair (cta_group::2) kernel: opt-in with RN_B200_CTA2=1.  It is parity-tested, but measured 2.98 ms vs
+  // 2.50 ms for the single-CTA form at B=640: the ALU-pipe-bound epilogue, not operand traffic, is the limiter.
+  static const bool allow_pair = []() { const char* e = getenv("RN_B200_CTA2"); return e && e[0] == '1'; }();
+  if (allow_pair && p.num_tiles % 2 == 0 && p.num_tiles >= 2) {
+    const int pairs = std::min(p.num_tiles / 2, sm_count() / 2);
+    RN_CUDA(cudaFuncSetAttribute(rn_g_chain_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kFwdThreads);
+    cfg.dynamicSmemBytes = kSmemLaunch;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RN_CUDA(cudaLaunchKernelEx(&cfg, rn_g_chain_kernel<MODE, true>, p));
+    RN_LAUNCH_CHECK("rn_g_chain_kernel<pair>");
+    return RN_OK;
+  }
   const int grid = std::min(p.num_tiles, sm_count());
-  RN_CUDA(cudaFuncSetAttribute(rn_g_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
-  rn_g_chain_kernel<MODE><<<grid, kChainThreads, kSmemLaunch, st>>>(p);
+  RN_CUDA(cudaFuncSetAttribute(rn_g_chain_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+  rn_g_chain_kernel<MODE, false><<<grid, kFwdThreads, kSmemLaunch, st>>>(p);
   RN_LAUNCH_CHECK("rn_g_chain_kernel");
   return RN_OK;
 }
@@ -852,7 +895,6 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
   p.dxg = dxg;
   p.scale = ws.scale;
   p.dZ = ws.dZ;
-  p.colpart = ws.colpart;
   RN_TRY(launch_chain<kDgrad>(p, st));
 
   // weight gradients of g layers 1..3: dW_l = dZ_{l+1}^T H_l
@@ -865,6 +907,7 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
     wp.H = reinterpret_cast<const char*>(sv.saveH) + (size_t)(l - 1) * kATile;    // H_l
     wp.h_stride = (size_t)3 * kATile;
     wp.partial = ws.partial;
+    wp.colpart = ws.colpart + (size_t)(l - 1) * tiles * kG;
     wp.num_tiles = tiles;
     rn_g_wgrad_kernel<<<wgrid, kWgThreads, kWgSmemLaunch, st>>>(wp);
     RN_LAUNCH_CHECK("rn_g_wgrad_kernel");
@@ -872,7 +915,7 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
     RN_LAUNCH_CHECK("wgrad_reduce_kernel");
     // bias gradient and question-injection gradients from the column sums of dZ_{l+1}
     float* delta = ws.delta + (size_t)(l - 1) * s.B * kG;
-    RN_TRY(colsum(ws.colpart + (size_t)(l - 1) * tiles * 4 * kG, delta, kG, s.B, 1, (long long)tps * 4, 0, 1, tps * 4, st));
+    RN_TRY(colsum(ws.colpart + (size_t)(l - 1) * tiles * kG, delta, kG, s.B, 1, (long long)tps, 0, 1, tps, st));
     const long long nd = (long long)s.B * kG;
     scale_inplace_kernel<<<cdiv(nd, 256), 256, 0, st>>>(delta, nd, ws.scale);
     RN_LAUNCH_CHECK("scale_inplace_kernel");

@@ -208,9 +208,48 @@ static __global__ void colsum_kernel(const float* __restrict__ A, float* __restr
   }
 }
 
+// float4 variant for wide rows (N % 4 == 0): block = 64 column groups x 4 row lanes, 1 KB coalesced row segments
+static __global__ void __launch_bounds__(256)
+colsum4_kernel(const float* __restrict__ A, float* __restrict__ out, int N, int n2, long long s1, long long s2,
+               long long si, int count) {
+  __shared__ float4 red[4][64];
+  const int cg = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int col = (blockIdx.y * 64 + cg) * 4;
+  const int g = blockIdx.x;
+  const int g1 = g / n2, g2 = g % n2;
+  const float* base = A + (g1 * s1 + g2 * s2) * N;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < N) {
+    int i = rl;
+    for (; i + 4 < count; i += 8) {       // two independent loads in flight
+      const float4 v0 = *reinterpret_cast<const float4*>(base + i * si * N + col);
+      const float4 v1 = *reinterpret_cast<const float4*>(base + (i + 4) * si * N + col);
+      acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+      acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+    }
+    for (; i < count; i += 4) {
+      const float4 v0 = *reinterpret_cast<const float4*>(base + i * si * N + col);
+      acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+    }
+  }
+  red[rl][cg] = acc;
+  __syncthreads();
+  if (rl == 0 && col < N) {
+    float4 v = red[0][cg];
+#pragma unroll
+    for (int y = 1; y < 4; ++y) { v.x += red[y][cg].x; v.y += red[y][cg].y; v.z += red[y][cg].z; v.w += red[y][cg].w; }
+    *reinterpret_cast<float4*>(out + (long long)g * N + col) = v;
+  }
+}
+
 inline int colsum(const float* A, float* out, int N, int n1, int n2, long long s1, long long s2, long long si,
                   int count, cudaStream_t st) {
   if (n1 * n2 <= 0) return RN_OK;
+  if (N % 4 == 0 && N >= 64 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    colsum4_kernel<<<dim3(n1 * n2, cdiv(N, 256)), 256, 0, st>>>(A, out, N, n2, s1, s2, si, count);
+    RN_LAUNCH_CHECK("colsum4_kernel");
+    return RN_OK;
+  }
   dim3 grid(n1 * n2, cdiv(N, 32)), block(32, 8);
   colsum_kernel<<<grid, block, 0, st>>>(A, out, N, n2, s1, s2, si, count);
   RN_LAUNCH_CHECK("colsum_kernel");
