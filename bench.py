@@ -102,6 +102,16 @@ def synthetic_batch(B: int, seed: int):
 # pairs + autograd) on the host cores.  The reference is Python and cannot travel to the GPU box, so this
 # is kind="port" (oracle/rn_oracle.py, pinned to the reference by tests/golden).
 # --------------------------------------------------------------------------------------------------
+def cpu_model_name() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_port_qps(sample_B: int, steps: int, warmup: int):
     from oracle import rn_oracle as O
 
@@ -143,7 +153,8 @@ def run_reference(args):
             "steps": steps, "warmup": 1, "ms_per_step": best * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "original-fp training step, 128x128 images, 8x8 grid, 4096 pairs/sample, batch 640 (timed on a batch-64 sample)"},
-            "cpu_baseline": {"value": qps, "unit": "questions/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": qps, "unit": "questions/s", "cores": cores, "cpu": cpu_model_name(), "kind": "port",
+                             "sample": sample},
             "e2e": {"value": qps, "unit": "questions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -217,7 +228,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     rel_ms = ops.timers_collect()           # {'relation_fwd': [...], 'relation_bwd': [...]}
     ops.timers_enable(False)
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
 
     # ---- end to end: pinned host inputs copied every step, loss read back every step ----------------
     copy_stream = torch.cuda.Stream()
@@ -243,7 +254,7 @@ def run_ours(args):
             torch.cuda.current_stream().wait_event(ready[slot])
             l = train_step(model, opt, *bufs[slot])
             consumed[slot].record()
-            losses.append(float(l))          # device -> host read of the step's result, every step
+            losses.append(float(l.detach()))  # device -> host read of the step's result, every step
         return losses
 
     for ev in consumed:
@@ -297,7 +308,7 @@ def run_ours(args):
         }
         if args.cpu_baseline:
             qps, cores, best = cpu_port_qps(64, 2, 1)
-            line["cpu_baseline"] = {"value": qps, "unit": "questions/s", "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": qps, "unit": "questions/s", "cores": cores, "cpu": cpu_model_name(), "kind": "port",
                                     "sample": "2 timed full training steps at batch 64 of the batch-640 workload (oracle port, "
                                               "PyTorch CPU, materialised pairs), best step"}
         print(json.dumps(line))

@@ -18,6 +18,24 @@ import torch.nn.functional as F
 from . import ops
 
 
+def shard_rows(n: int, rank: int, world: int) -> slice:
+    """Rows of a global batch owned by `rank`: contiguous equal shards, rank r takes [r*n/W, (r+1)*n/W)
+    (the DataParallel-equivalent split of train.py:256-258)."""
+    if n % world:
+        raise ValueError(f"global batch {n} is not divisible by world size {world}")
+    per = n // world
+    return slice(rank * per, (rank + 1) * per)
+
+
+def allreduce_flat_(flat: torch.Tensor) -> float:
+    """The single exchange step of the path: sum-all-reduce of the flat gradient buffer (NCCL on GPUs, gloo in
+    the CPU tests).  Returns the scale (1/world) the optimiser applies so the result is the mean over ranks."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        return 1.0 / dist.get_world_size()
+    return 1.0
+
+
 class FlatClipAdam:
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 5e-6, weight_decay: float = 1e-4,
                  clip_norm: float = 50.0, betas=(0.9, 0.999), eps: float = 1e-8):
@@ -54,10 +72,7 @@ class FlatClipAdam:
 
     def step(self) -> torch.Tensor:
         g = self.gather_grads()
-        scale = 1.0
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM)          # the single exchange step of the path
-            scale = 1.0 / dist.get_world_size()
+        scale = allreduce_flat_(g)
         self.step_count += 1
         self.last_norm = ops.clip_adam_(self.flat, g, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
                                         self.clip_norm, self.weight_decay, self.betas, self.eps, grad_scale=scale)
