@@ -166,7 +166,6 @@ def run_ours(args):
     import relationnetworks_clevr_b200 as R
     from relationnetworks_clevr_b200 import _lib, ops
     from relationnetworks_clevr_b200.trainer import FlatClipAdam, train_step
-    from oracle import rn_oracle as O      # only for HYPERPARAMS/seeded_params (inputs), never on the timed path
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -185,12 +184,12 @@ def run_ours(args):
     class A:
         qdict_size, adict_size = QDICT, ADICT
 
-    hyp = O.HYPERPARAMS[CONFIG]
+    hyp = json.load(open(os.path.join(ROOT, "config.json")))["hyperparams"][CONFIG]
     import contextlib
     import io
+    torch.manual_seed(42)                       # train.py:382 -- identical random init on all ranks
     with contextlib.redirect_stdout(io.StringIO()):
         model = R.RN(A, hyp)
-    model.load_state_dict(O.seeded_params(hyp, QDICT, ADICT, seed=42), strict=False)   # identical init on all ranks
     model.to(dev).train()
     model.rl.precision = args.precision
     opt = FlatClipAdam(model.parameters(), lr=5e-6, weight_decay=1e-4, clip_norm=50.0)
