@@ -207,12 +207,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -------------------------------------------------------------------
-    for i in range(args.warmup):
-        train_step(model, opt, *resident[i % n_batches])
-    barrier()
+    # the clock sampler (an nvidia-smi subprocess) is started BEFORE the warm-up: its start-up stalls driver
+    # calls for ~100 ms, which must not land inside the timed region; it keeps sampling through it
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        train_step(model, opt, *resident[i % n_batches])
+    barrier()
+    if rank == 0:
+        sampler.rows.clear()
     ops.timers_enable(True)
     launches0 = _lib.lib().rn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -318,8 +322,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=640)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])

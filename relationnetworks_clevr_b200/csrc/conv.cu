@@ -30,7 +30,9 @@ __device__ __forceinline__ float act_in(float y, const float* __restrict__ aff, 
 
 // ------------------------------------------------------------------------------------------
 // forward conv: y = conv(act(in)) + bias ; optional per-block (sum, sumsq) partials
-// grid (tiles, B), block 256 (16x16 output pixels, 24 channels per thread)
+// grid (tiles, B), block 256 = 64 quads (2x2 output pixels) x 4 channel groups (6 channels):
+// 24 accumulators per thread; per input channel 25 input LDS + 18 broadcast weight LDS.128 feed 216 FFMA.
+// Warp = 8 quads (x) x 4 channel groups: input reads hit 8 distinct banks and broadcast over the groups.
 // ------------------------------------------------------------------------------------------
 template <int CIN>
 __global__ void __launch_bounds__(256)
@@ -42,15 +44,18 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, 
   __shared__ __align__(16) float wsm[CC][kC][12];
   __shared__ float red[8][2 * kC];
 
-  const int tid = threadIdx.x, tx = tid % kTile, ty = tid / kTile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qx = lane & 7, cg = lane >> 3, qy = warp;       // quad (qy, qx), channels [6*cg, 6*cg + 6)
   const int b = blockIdx.y;
   const int oh0 = (blockIdx.x / tiles_x) * kTile, ow0 = (blockIdx.x % tiles_x) * kTile;
   const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
   const float* inb = in + (size_t)b * CIN * hin * hin;
 
-  float acc[kC];
+  float acc[4][6];
 #pragma unroll
-  for (int co = 0; co < kC; ++co) acc[co] = 0.f;
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[p][c] = 0.f;
 
   for (int ci0 = 0; ci0 < CIN; ci0 += CC) {
     __syncthreads();
@@ -70,43 +75,58 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, 
     __syncthreads();
 #pragma unroll 1
     for (int ci = 0; ci < CC; ++ci) {
-      float xv[9];
+      float xv[5][5];
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
+      for (int r = 0; r < 5; ++r)
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) xv[kh * 3 + kw] = patch[ci][2 * ty + kh][2 * tx + kw];
+        for (int c = 0; c < 5; ++c) xv[r][c] = patch[ci][4 * qy + r][4 * qx + c];
 #pragma unroll
-      for (int co = 0; co < kC; ++co) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[ci][co][0]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[ci][co][4]);
-        const float w8 = wsm[ci][co][8];
-        float a = acc[co];
-        a = fmaf(xv[0], w0.x, a); a = fmaf(xv[1], w0.y, a); a = fmaf(xv[2], w0.z, a);
-        a = fmaf(xv[3], w0.w, a); a = fmaf(xv[4], w1.x, a); a = fmaf(xv[5], w1.y, a);
-        a = fmaf(xv[6], w1.z, a); a = fmaf(xv[7], w1.w, a); a = fmaf(xv[8], w8, a);
-        acc[co] = a;
+      for (int c = 0; c < 6; ++c) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[ci][cg * 6 + c][0]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[ci][cg * 6 + c][4]);
+        const float w8 = wsm[ci][cg * 6 + c][8];
+        const float wt[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w8};
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+          for (int px = 0; px < 2; ++px) {
+            float a = acc[py * 2 + px][c];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) a = fmaf(xv[2 * py + kh][2 * px + kw], wt[kh * 3 + kw], a);
+            acc[py * 2 + px][c] = a;
+          }
       }
     }
   }
 
-  const int oh = oh0 + ty, ow = ow0 + tx;
-  const bool valid = oh < hout && ow < hout;
+  const int oh = oh0 + 2 * qy, ow = ow0 + 2 * qx;
+  const bool valid = oh < hout && ow < hout;        // hout is even: a quad is entirely in or out
   float* yb = y + (size_t)b * kC * hout * hout;
+  float s1[6], s2[6];
 #pragma unroll
-  for (int co = 0; co < kC; ++co) {
-    acc[co] += bias[co];
-    if (valid) yb[((size_t)co * hout + oh) * hout + ow] = acc[co];
+  for (int c = 0; c < 6; ++c) {
+    const int co = cg * 6 + c;
+    const float bv = bias[co];
+    const float v00 = acc[0][c] + bv, v01 = acc[1][c] + bv, v10 = acc[2][c] + bv, v11 = acc[3][c] + bv;
+    if (valid) {
+      *reinterpret_cast<float2*>(&yb[((size_t)co * hout + oh) * hout + ow]) = make_float2(v00, v01);
+      *reinterpret_cast<float2*>(&yb[((size_t)co * hout + oh + 1) * hout + ow]) = make_float2(v10, v11);
+    }
+    s1[c] = valid ? (v00 + v01) + (v10 + v11) : 0.f;
+    s2[c] = valid ? (v00 * v00 + v01 * v01) + (v10 * v10 + v11 * v11) : 0.f;
   }
   if (stat_part) {
-    const int lane = tid % 32, warp = tid / 32;
 #pragma unroll
-    for (int co = 0; co < kC; ++co) {
-      float s = valid ? acc[co] : 0.f, s2 = s * s;
-      for (int o = 16; o; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    for (int c = 0; c < 6; ++c) {
+      float a = s1[c], a2 = s2[c];
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {                 // over the 8 quads that share this channel group
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
       }
-      if (lane == 0) { red[warp][co] = s; red[warp][kC + co] = s2; }
+      if (qx == 0) { red[warp][cg * 6 + c] = a; red[warp][kC + cg * 6 + c] = a2; }
     }
     __syncthreads();
     if (tid < 2 * kC) {
@@ -342,6 +362,103 @@ conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff
 }
 
 // ------------------------------------------------------------------------------------------
+// weight gradient, 24 input channels (layers 2..4): per-block partial dW[24][24][9] over a 16x16 tile of dy.
+// grid (tiles, B), block 256 = 8 pixel partitions (one warp each) x 4 output-channel groups (6) x 8 input
+// channels: 54 accumulators per thread; per pixel 3 LDS.64 (dy, pixel-major, broadcast over ci) + 9 input LDS
+// (broadcast over the channel groups) feed 54 FFMA.  Partitions are combined by a 3-round tree in smem.
+// ------------------------------------------------------------------------------------------
+constexpr int kWg2RedFloats = 4 * 32 * 54;
+static size_t wgrad24_smem_bytes() {
+  return ((size_t)kChunk * kPatch * kPatch + (size_t)kTile * kTile * kC) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(256)
+conv_wgrad24_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ dy,
+                    float* __restrict__ part, int hin, int hout, int tiles_x) {
+  extern __shared__ __align__(16) float wg_smem[];
+  float (*patch)[kPatch][kPatch] = reinterpret_cast<float (*)[kPatch][kPatch]>(wg_smem);       // [8][33][33]
+  float* red = wg_smem;                                          // aliases the patch between channel chunks
+  float (*dys)[kC] = reinterpret_cast<float (*)[kC]>(wg_smem + kChunk * kPatch * kPatch);      // [256][24]
+  static_assert(kWg2RedFloats <= kChunk * kPatch * kPatch, "reduction buffer must fit in the patch");
+
+  const int tid = threadIdx.x, lane = tid & 31, pp = tid >> 5;
+  const int cg = lane >> 3, ci = lane & 7;
+  const int b = blockIdx.y;
+  const int oh0 = (blockIdx.x / tiles_x) * kTile, ow0 = (blockIdx.x % tiles_x) * kTile;
+  const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
+  const float* inb = in + (size_t)b * kC * hin * hin;
+  const float* dyb = dy + (size_t)b * kC * hout * hout;
+  float* out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kC * kC * 9);
+
+  for (int idx = tid; idx < kC * kTile * kTile; idx += 256) {      // coalesced read, pixel-major store
+    const int co = idx / (kTile * kTile), p = idx % (kTile * kTile);
+    const int oh = oh0 + p / kTile, ow = ow0 + p % kTile;
+    dys[p][co] = (oh < hout && ow < hout) ? dyb[((size_t)co * hout + oh) * hout + ow] : 0.f;
+  }
+
+  for (int ci0 = 0; ci0 < kC; ci0 += kChunk) {
+    __syncthreads();
+    for (int idx = tid; idx < kChunk * kPatch * kPatch; idx += 256) {
+      const int cc = idx / (kPatch * kPatch), rem = idx % (kPatch * kPatch);
+      const int r = rem / kPatch, c = rem % kPatch;
+      const int ih = ih0 + r, iw = iw0 + c;
+      float v = 0.f;
+      if (ih >= 0 && ih < hin && iw >= 0 && iw < hin) v = act_in(inb[((size_t)(ci0 + cc) * hin + ih) * hin + iw], in_aff, ci0 + cc);
+      patch[cc][r][c] = v;
+    }
+    __syncthreads();
+    float acc[6][9];
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
+#pragma unroll 2
+    for (int p = pp; p < kTile * kTile; p += 8) {
+      const int py = p / kTile, px = p % kTile;
+      float xv[9];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) xv[kh * 3 + kw] = patch[ci][2 * py + kh][2 * px + kw];
+      const float2 g0 = *reinterpret_cast<const float2*>(&dys[p][cg * 6]);
+      const float2 g1 = *reinterpret_cast<const float2*>(&dys[p][cg * 6 + 2]);
+      const float2 g2 = *reinterpret_cast<const float2*>(&dys[p][cg * 6 + 4]);
+      const float g[6] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y};
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(g[j], xv[t], acc[j][t]);
+    }
+    // combine the 8 pixel partitions: 4..7 -> 0..3, 2..3 -> 0..1, 1 -> 0 (fixed order: deterministic)
+#pragma unroll
+    for (int half = 4; half >= 1; half >>= 1) {
+      __syncthreads();               // previous readers of `red` (or of the patch it aliases) are done
+      if (pp >= half && pp < 2 * half) {
+        float* dst = red + ((size_t)(pp - half) * 32 + lane) * 54;
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) dst[j * 9 + t] = acc[j][t];
+      }
+      __syncthreads();
+      if (pp < half) {
+        const float* src = red + ((size_t)pp * 32 + lane) * 54;
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[j][t] += src[j * 9 + t];
+      }
+    }
+    if (pp == 0) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) out[((size_t)(cg * 6 + j) * kC + ci0 + ci) * 9 + t] = acc[j][t];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // data gradient (layers 2..4): dA_prev[b, ci, ih, iw] = sum_{co,kh,kw} dy[b, co, oh, ow] W[co, ci, kh, kw]
 // with ih = 2*oh + kh - 1.  Block: 32x32 input pixels of one image, thread = 2x2 input quad x 8 ci.
 // grid (tiles, B, 3 ci-chunks), block 256
@@ -545,9 +662,9 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float
       RN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       conv_wgrad_kernel<3><<<grid, 256, smem, st>>>(in, in_aff, dy, wpart, hin, hout, tx);
     } else {
-      const size_t smem = wgrad_smem_bytes(kChunk);
-      RN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conv_wgrad_kernel<kC><<<grid, 256, smem, st>>>(in, in_aff, dy, wpart, hin, hout, tx);
+      const size_t smem = wgrad24_smem_bytes();
+      RN_CUDA(cudaFuncSetAttribute(conv_wgrad24_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv_wgrad24_kernel<<<grid, 256, smem, st>>>(in, in_aff, dy, wpart, hin, hout, tx);
     }
     RN_LAUNCH_CHECK("conv_wgrad_kernel");
     RN_TRY(colsum(wpart, Gr[l].dw, kC * cin * 9, 1, 1, 0, 0, 1, p.tiles[l] * cfg->B, st));
