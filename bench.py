@@ -308,6 +308,7 @@ def run_ours(args):
                          "relation_fwd_ms": fwd_ms, "relation_bwd_ms": bwd_ms,
                          "algorithmic_flop_per_launch_pair": G_FLOP_TRAIN * B, "peak_source": peaks["source"] + " (sustained bf16)"},
             "final_loss": final_loss,
+            "op_ms": {k: statistics.mean(v) for k, v in rel_ms.items()},
         }
         if args.cpu_baseline:
             qps, cores, best = cpu_port_qps(64, 2, 1)

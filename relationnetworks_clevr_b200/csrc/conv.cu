@@ -28,6 +28,55 @@ __device__ __forceinline__ float act_in(float y, const float* __restrict__ aff, 
   return aff ? fmaxf(fmaf(aff[2 * kC + c], y, aff[3 * kC + c]), 0.f) : y;
 }
 
+// ---- asynchronous staging (LDGSTS): every thread keeps ALL its 4-byte copies of a patch in flight at once,
+// so the L2/HBM round trip is paid once per patch instead of once per element -------------------------------
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 4 : 0;                    // src-size 0: nothing is read, the 4 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Stage a [CC][33][33] input patch (zero padding outside the image) and apply the previous layer's
+// BatchNorm affine + ReLU in place.  Each thread transforms exactly the elements it copied, so no barrier is
+// needed between the wait and the transform; the caller synchronises before the patch is consumed.
+template <int CC>
+__device__ __forceinline__ void stage_patch_issue(float (*patch)[kPatch][kPatch], const float* __restrict__ inb, int ci0,
+                                                  int ih0, int iw0, int hin, int tid) {
+#pragma unroll 4
+  for (int idx = tid; idx < CC * kPatch * kPatch; idx += 256) {
+    const int ci = idx / (kPatch * kPatch), rem = idx % (kPatch * kPatch);
+    const int r = rem / kPatch, c = rem % kPatch;
+    const int ih = ih0 + r, iw = iw0 + c;
+    const bool valid = ih >= 0 && ih < hin && iw >= 0 && iw < hin;
+    cp_async4(&patch[ci][r][c], valid ? inb + ((size_t)(ci0 + ci) * hin + ih) * hin + iw : inb, valid);
+  }
+}
+
+template <int CC>
+__device__ __forceinline__ void stage_patch_finish(float (*patch)[kPatch][kPatch], const float* __restrict__ in_aff,
+                                                   int ci0, int ih0, int iw0, int hin, int tid) {
+  cp_async_wait_all();
+  if (in_aff) {
+#pragma unroll 4
+    for (int idx = tid; idx < CC * kPatch * kPatch; idx += 256) {
+      const int ci = idx / (kPatch * kPatch), rem = idx % (kPatch * kPatch);
+      const int r = rem / kPatch, c = rem % kPatch;
+      const int ih = ih0 + r, iw = iw0 + c;
+      if (ih >= 0 && ih < hin && iw >= 0 && iw < hin)      // the zero padding applies to the post-activation tensor
+        patch[ci][r][c] = act_in(patch[ci][r][c], in_aff, ci0 + ci);
+    }
+  }
+}
+
+template <int CC>
+__device__ __forceinline__ void stage_patch(float (*patch)[kPatch][kPatch], const float* __restrict__ inb,
+                                            const float* __restrict__ in_aff, int ci0, int ih0, int iw0, int hin,
+                                            int tid) {
+  stage_patch_issue<CC>(patch, inb, ci0, ih0, iw0, hin, tid);
+  stage_patch_finish<CC>(patch, in_aff, ci0, ih0, iw0, hin, tid);
+}
+
 // ------------------------------------------------------------------------------------------
 // forward conv: y = conv(act(in)) + bias ; optional per-block (sum, sumsq) partials
 // grid (tiles, B), block 256 = 64 quads (2x2 output pixels) x 4 channel groups (6 channels):
@@ -39,9 +88,13 @@ __global__ void __launch_bounds__(256)
 conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ w,
                 const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ stat_part, int hin,
                 int hout, int tiles_x) {
-  constexpr int CC = CIN < kChunk ? CIN : kChunk;
-  __shared__ float patch[CC][kPatch][kPatch];
-  __shared__ __align__(16) float wsm[CC][kC][12];
+  // 24-channel layers: 4-channel chunks, double buffered -- the copies of chunk k+1 are in flight while
+  // chunk k is consumed.  The RGB layer is a single 3-channel chunk.
+  constexpr int CC = CIN < 4 ? CIN : 4;
+  constexpr int NBUF = CIN > CC ? 2 : 1;
+  constexpr int NCHUNK = CIN / CC;
+  __shared__ float patch[NBUF][CC][kPatch][kPatch];
+  __shared__ __align__(16) float wsm[NBUF][CC][kC][12];
   __shared__ float red[8][2 * kC];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -57,34 +110,34 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, 
 #pragma unroll
     for (int c = 0; c < 6; ++c) acc[p][c] = 0.f;
 
-  for (int ci0 = 0; ci0 < CIN; ci0 += CC) {
-    __syncthreads();
-    for (int idx = tid; idx < CC * kPatch * kPatch; idx += 256) {
-      const int ci = idx / (kPatch * kPatch), rem = idx % (kPatch * kPatch);
-      const int r = rem / kPatch, c = rem % kPatch;
-      const int ih = ih0 + r, iw = iw0 + c;
-      float v = 0.f;      // zero padding applies to the post-activation tensor
-      if (ih >= 0 && ih < hin && iw >= 0 && iw < hin) v = act_in(inb[((size_t)(ci0 + ci) * hin + ih) * hin + iw], in_aff, ci0 + ci);
-      patch[ci][r][c] = v;
-    }
+  auto issue = [&](int k) {
+    const int buf = k % NBUF, ci0 = k * CC;
+    stage_patch_issue<CC>(patch[buf], inb, ci0, ih0, iw0, hin, tid);
     for (int idx = tid; idx < CC * kC * 9; idx += 256) {
       const int ci = idx / (kC * 9), rem = idx % (kC * 9);
       const int co = rem / 9, t = rem % 9;
-      wsm[ci][co][t] = w[((size_t)co * CIN + ci0 + ci) * 9 + t];
+      cp_async4(&wsm[buf][ci][co][t], w + ((size_t)co * CIN + ci0 + ci) * 9 + t, true);
     }
-    __syncthreads();
+  };
+
+  issue(0);
+  for (int k = 0; k < NCHUNK; ++k) {
+    const int buf = k % NBUF;
+    stage_patch_finish<CC>(patch[buf], in_aff, k * CC, ih0, iw0, hin, tid);
+    __syncthreads();              // chunk k is complete; everyone is done reading the other buffer
+    if (k + 1 < NCHUNK) issue(k + 1);
 #pragma unroll 1
     for (int ci = 0; ci < CC; ++ci) {
       float xv[5][5];
 #pragma unroll
       for (int r = 0; r < 5; ++r)
 #pragma unroll
-        for (int c = 0; c < 5; ++c) xv[r][c] = patch[ci][4 * qy + r][4 * qx + c];
+        for (int c = 0; c < 5; ++c) xv[r][c] = patch[buf][ci][4 * qy + r][4 * qx + c];
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[ci][cg * 6 + c][0]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[ci][cg * 6 + c][4]);
-        const float w8 = wsm[ci][cg * 6 + c][8];
+        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[buf][ci][cg * 6 + c][0]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[buf][ci][cg * 6 + c][4]);
+        const float w8 = wsm[buf][ci][cg * 6 + c][8];
         const float wt[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w8};
 #pragma unroll
         for (int py = 0; py < 2; ++py)
@@ -144,12 +197,13 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int nblk, dou
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ aff, float eps, float momentum,
                                    int training) {
-  const int c = threadIdx.x / 32, lane = threadIdx.x % 32;
-  if (c >= kC) return;
+  // one 256-thread block per channel; fixed-order (thread-strided, then tree) double-precision reduction
+  __shared__ double sh[2][8];
+  const int c = blockIdx.x, lane = threadIdx.x % 32, wrp = threadIdx.x / 32;
   float mean, var;
   if (training) {
     double s = 0.0, s2 = 0.0;
-    for (int i = lane; i < nblk; i += 32) {
+    for (int i = threadIdx.x; i < nblk; i += 256) {
       s += part[(size_t)i * 2 * kC + c];
       s2 += part[(size_t)i * 2 * kC + kC + c];
     }
@@ -157,12 +211,16 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int nblk, dou
       s += __shfl_xor_sync(0xffffffffu, s, o);
       s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
+    if (lane == 0) { sh[0][wrp] = s; sh[1][wrp] = s2; }
+    __syncthreads();
+    s = 0.0; s2 = 0.0;
+    for (int i = 0; i < 8; ++i) { s += sh[0][i]; s2 += sh[1][i]; }
     const double m = s / count;
     double v = s2 / count - m * m;
     if (v < 0) v = 0;
     mean = (float)m;
     var = (float)v;
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(v * (count / (count > 1 ? count - 1 : 1)));
     }
@@ -170,7 +228,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int nblk, dou
     mean = running_mean[c];
     var = running_var[c];
   }
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
     const float rstd = rsqrtf(var + eps);
     const float sc = gamma[c] * rstd;
     aff[c] = mean;
@@ -304,6 +362,7 @@ conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff
   const float* dyb = dy + (size_t)b * kC * hout * hout;
   float* out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kC * CIN * 9);
 
+#pragma unroll 8
   for (int idx = tid; idx < kC * kTile * kTile; idx += 256) {
     const int co = idx / (kTile * kTile), p = idx % (kTile * kTile);
     const int oh = oh0 + p / kTile, ow = ow0 + p % kTile;
@@ -314,14 +373,7 @@ conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff
 
   for (int ci0 = 0; ci0 < CIN; ci0 += CC) {
     __syncthreads();
-    for (int idx = tid; idx < CC * kPatch * kPatch; idx += 256) {
-      const int cc = idx / (kPatch * kPatch), rem = idx % (kPatch * kPatch);
-      const int r = rem / kPatch, c = rem % kPatch;
-      const int ih = ih0 + r, iw = iw0 + c;
-      float v = 0.f;
-      if (ih >= 0 && ih < hin && iw >= 0 && iw < hin) v = act_in(inb[((size_t)(ci0 + cc) * hin + ih) * hin + iw], in_aff, ci0 + cc);
-      patch[cc][r][c] = v;
-    }
+    stage_patch<CC>(patch, inb, in_aff, ci0, ih0, iw0, hin, tid);
     __syncthreads();
     if (active) {
       float acc[4][9];
@@ -390,6 +442,7 @@ conv_wgrad24_kernel(const float* __restrict__ in, const float* __restrict__ in_a
   const float* dyb = dy + (size_t)b * kC * hout * hout;
   float* out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kC * kC * 9);
 
+#pragma unroll 8
   for (int idx = tid; idx < kC * kTile * kTile; idx += 256) {      // coalesced read, pixel-major store
     const int co = idx / (kTile * kTile), p = idx % (kTile * kTile);
     const int oh = oh0 + p / kTile, ow = ow0 + p % kTile;
@@ -398,14 +451,7 @@ conv_wgrad24_kernel(const float* __restrict__ in, const float* __restrict__ in_a
 
   for (int ci0 = 0; ci0 < kC; ci0 += kChunk) {
     __syncthreads();
-    for (int idx = tid; idx < kChunk * kPatch * kPatch; idx += 256) {
-      const int cc = idx / (kPatch * kPatch), rem = idx % (kPatch * kPatch);
-      const int r = rem / kPatch, c = rem % kPatch;
-      const int ih = ih0 + r, iw = iw0 + c;
-      float v = 0.f;
-      if (ih >= 0 && ih < hin && iw >= 0 && iw < hin) v = act_in(inb[((size_t)(ci0 + cc) * hin + ih) * hin + iw], in_aff, ci0 + cc);
-      patch[cc][r][c] = v;
-    }
+    stage_patch<kChunk>(patch, inb, in_aff, ci0, ih0, iw0, hin, tid);
     __syncthreads();
     float acc[6][9];
 #pragma unroll
@@ -473,6 +519,7 @@ conv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, flo
   const int q0y = (blockIdx.x / tiles_x) * kTile, q0x = (blockIdx.x % tiles_x) * kTile;   // quad == output coords
   const float* dyb = dy + (size_t)b * kC * hout * hout;
 
+#pragma unroll 8
   for (int idx = tid; idx < kC * (kTile + 1) * (kTile + 1); idx += 256) {
     const int co = idx / ((kTile + 1) * (kTile + 1)), rem = idx % ((kTile + 1) * (kTile + 1));
     const int r = rem / (kTile + 1), c = rem % (kTile + 1);
@@ -526,6 +573,8 @@ static size_t wgrad_smem_bytes(int cc) {
   return ((size_t)cc * kPatch * kPatch + (size_t)kC * kTile * kTile + (size_t)5 * 6 * cc * 37) * sizeof(float);
 }
 
+constexpr int kRedChunks = 64;      // row chunks of the two-stage fixed-order reduction of the wgrad partials
+
 struct ConvPlan {
   int h[RN_CONV_LAYERS + 1];        // h[0] = side, h[l+1] = output edge of layer l
   size_t y_off[RN_CONV_LAYERS];     // float offsets of y_l in `saved`
@@ -559,7 +608,8 @@ static ConvPlan make_plan(const rn_conv_cfg& c) {
     wpart = std::max(wpart, (size_t)c.B * p.tiles[l] * kC * cin * 9);
     spart = std::max(spart, (size_t)c.B * p.tiles[l] * 2 * kC);
   }
-  p.scratch_floats = 2 * big + round_up(std::max(spart, (size_t)c.B * kC * 2), 64) + 64 * 4 + round_up(wpart, 64);
+  p.scratch_floats = 2 * big + round_up(std::max(spart, (size_t)c.B * kC * 2), 64) + 64 * 4 + round_up(wpart, 64) +
+                     (size_t)kRedChunks * kC * kC * 9;
   return p;
 }
 
@@ -604,7 +654,7 @@ extern "C" int rn_conv_fwd(const rn_conv_cfg* cfg, const float* img, const rn_co
     else
       conv_fwd_kernel<kC><<<grid, 256, 0, st>>>(in, in_aff, L[l].w, L[l].bias, y, part, hin, hout, tx);
     RN_LAUNCH_CHECK("conv_fwd_kernel");
-    bn_finalize_kernel<<<1, 32 * kC, 0, st>>>(scratch, p.tiles[l] * cfg->B, (double)cfg->B * hout * hout, L[l].gamma,
+    bn_finalize_kernel<<<kC, 256, 0, st>>>(scratch, p.tiles[l] * cfg->B, (double)cfg->B * hout * hout, L[l].gamma,
                                              L[l].beta, L[l].running_mean, L[l].running_var, aff, cfg->eps,
                                              cfg->momentum, cfg->training);
     RN_LAUNCH_CHECK("bn_finalize_kernel");
@@ -632,6 +682,9 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float
   for (int l = 0; l < RN_CONV_LAYERS; ++l) spart = std::max(spart, (size_t)cfg->B * p.tiles[l] * 2 * kC);
   float* coef = bnpart + round_up(std::max(spart, (size_t)cfg->B * kC * 2), 64);
   float* wpart = coef + 64 * 4;
+  size_t wpart_floats = 0;
+  for (int l = 0; l < RN_CONV_LAYERS; ++l)
+    wpart_floats = std::max(wpart_floats, (size_t)cfg->B * p.tiles[l] * kC * (l == 0 ? 3 : kC) * 9);
 
   const int d = p.h[RN_CONV_LAYERS];
   {
@@ -667,7 +720,23 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float
       conv_wgrad24_kernel<<<grid, 256, smem, st>>>(in, in_aff, dy, wpart, hin, hout, tx);
     }
     RN_LAUNCH_CHECK("conv_wgrad_kernel");
-    RN_TRY(colsum(wpart, Gr[l].dw, kC * cin * 9, 1, 1, 0, 0, 1, p.tiles[l] * cfg->B, st));
+    {
+      // dW = sum over blocks of the partials, two stages so the reduction itself fills the machine:
+      // [nblk][N] -> [64][N] -> [N]  (both fixed order: deterministic)
+      const int N = kC * cin * 9, nblk = p.tiles[l] * cfg->B;
+      float* red_tmp = wpart + round_up((size_t)wpart_floats, 64);
+      if (nblk >= 4 * kRedChunks) {
+        const int per = cdiv(nblk, kRedChunks);
+        const int chunks = cdiv(nblk, per);
+        // rows [c*per, min(nblk, (c+1)*per)): the last chunk may be short -> handle it with a second call
+        const int full = nblk / per;
+        RN_TRY(colsum(wpart, red_tmp, N, full, 1, per, 0, 1, per, st));
+        if (chunks > full) RN_TRY(colsum(wpart + (size_t)full * per * N, red_tmp + (size_t)full * N, N, 1, 1, 0, 0, 1, nblk - full * per, st));
+        RN_TRY(colsum(red_tmp, Gr[l].dw, N, 1, 1, 0, 0, 1, chunks, st));
+      } else {
+        RN_TRY(colsum(wpart, Gr[l].dw, N, 1, 1, 0, 0, 1, nblk, st));
+      }
+    }
     if (l > 0) {
       // data gradient into dA (now sized for layer l-1's output == this layer's input)
       const int qt = cdiv(hout, kTile);

@@ -164,8 +164,9 @@ class FHeadFunction(torch.autograd.Function):
         mask_ptr = drop_mask.data_ptr() if drop_mask is not None else None
         if drop_mask is not None and (drop_mask.dtype != torch.uint8 or tuple(drop_mask.shape) != (B, F2)):
             raise RuntimeError("drop_mask must be uint8 [B, F2]")
-        check(lib().rn_f_fwd(C.byref(cfg), *[v.data_ptr() for v in t], mask_ptr, logp.data_ptr(), saved.data_ptr(),
-                             _stream()), "rn_f_fwd")
+        with _Timed("f_fwd"):
+            check(lib().rn_f_fwd(C.byref(cfg), *[v.data_ptr() for v in t], mask_ptr, logp.data_ptr(), saved.data_ptr(),
+                                 _stream()), "rn_f_fwd")
         ctx.cfg = cfg
         ctx.has_mask = drop_mask is not None
         ctx.save_for_backward(logp, saved, t[0], t[1], t[3], t[5], drop_mask if drop_mask is not None else logp)
@@ -225,8 +226,9 @@ class ConvObjectsFunction(torch.autograd.Function):
         d = side // 16
         objects = torch.empty(B, d * d, 26, dtype=torch.float32, device=img.device)
         layers = _conv_layers(ps, running)
-        check(lib().rn_conv_fwd(C.byref(cfg), img_.data_ptr(), layers, objects.data_ptr(), saved.data_ptr(),
-                                scratch.data_ptr(), _stream()), "rn_conv_fwd")
+        with _Timed("conv_fwd"):
+            check(lib().rn_conv_fwd(C.byref(cfg), img_.data_ptr(), layers, objects.data_ptr(), saved.data_ptr(),
+                                    scratch.data_ptr(), _stream()), "rn_conv_fwd")
         if any(ctx.needs_input_grad):
             ctx.cfg = cfg
             ctx.saved_buf = saved
@@ -246,8 +248,9 @@ class ConvObjectsFunction(torch.autograd.Function):
             garr[l] = ConvGrads(*[g.data_ptr() for g in grads[4 * l: 4 * l + 4]])
         layers = _conv_layers(ps, ctx.running)
         scratch = _scratch_bytes(img_.device, "conv", ctx.scratch_floats * 4)
-        check(lib().rn_conv_bwd(C.byref(cfg), img_.data_ptr(), dobj.data_ptr(), layers, ctx.saved_buf.data_ptr(), garr,
-                                scratch.data_ptr(), _stream()), "rn_conv_bwd")
+        with _Timed("conv_bwd"):
+            check(lib().rn_conv_bwd(C.byref(cfg), img_.data_ptr(), dobj.data_ptr(), layers, ctx.saved_buf.data_ptr(),
+                                    garr, scratch.data_ptr(), _stream()), "rn_conv_bwd")
         return (None, None, None, None, None, *grads)
 
 
