@@ -330,3 +330,49 @@ def test_model_train_step_matches_reference_golden(stem, precision):
     for name, buf in m.named_buffers():
         if "running" in name:
             assert O.rel_err(buf.cpu(), torch.from_numpy(z["running/" + name])) < TOL_FP32
+
+
+@pytest.mark.parametrize("n", [144, 256])
+def test_relation_tcgen05_grid_sweep(n):
+    """BASELINE.json config 5 (d = 12, 16): tiles straddle `a` boundaries for n = 144; the reference needs 43 GB
+    per activation at B=640, d=16, so the check is tcgen05 vs this library's fp32 SIMT path (itself pinned to the
+    oracle above) at a small batch."""
+    B, k, Q, G, qinj = 2, 26, 128, 256, 0
+    assert ops.tc_supported(n, G, 4, k, Q, qinj)
+    gen = torch.Generator().manual_seed(n)
+    x = torch.randn(B, n, k, generator=gen).to(DEV)
+    q = torch.randn(B, Q, generator=gen).to(DEV)
+    dxg = torch.randn(B, G, generator=gen).to(DEV)
+    params = _g_params(n, k, Q, G, qinj, gen)
+    res = {}
+    for precision in ("fp32", "parity"):
+        xc, qc = x.clone().requires_grad_(True), q.clone().requires_grad_(True)
+        wb = []
+        for w, b in params:
+            wb += [w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)]
+        xg = ops.RelationFunction.apply(xc, qc, qinj, precision, *wb)
+        xg.backward(dxg)
+        res[precision] = [xg.detach(), xc.grad, qc.grad] + [t.grad for t in wb]
+    assert O.rel_err(res["parity"][0].cpu(), res["fp32"][0].cpu()) < TOL_PARITY
+    assert O.rel_err(res["parity"][1].cpu(), res["fp32"][1].cpu()) < TOL_TC_DX[0]
+    for a, b_ in zip(res["parity"][2:], res["fp32"][2:]):
+        assert O.rel_err(a.cpu(), b_.cpu()) < TOL_TC_PARAM[0]
+
+
+def test_train_driver_smoke(tmp_path):
+    """The reference-surface driver runs an epoch on synthetic CLEVR-shaped batches and writes RN_epoch_01.pth."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "train.py"), "--model", "original-fp", "--epochs", "1", "--batch-size", "32",
+           "--synthetic-batches", "3", "--log-interval", "1", "--config", os.path.join(root, "config.json")]
+    env = dict(os.environ, PYTHONPATH=root)
+    out = subprocess.run(cmd, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Train Epoch: 1 [0/96 (0%)] Train loss:" in out.stdout
+    assert "Test Epoch 1: Accuracy" in out.stdout
+    ckpts = [os.path.join(dp, f) for dp, _, fs in os.walk(tmp_path) for f in fs if f == "RN_epoch_01.pth"]
+    assert len(ckpts) == 1
+    sd = torch.load(ckpts[0], map_location="cpu", weights_only=True)
+    assert "rl.g_layers.0.weight" in sd and "conv.batchNorm1.running_mean" in sd
