@@ -150,9 +150,20 @@ __device__ __forceinline__ uint32_t pack_relu_half2(float lo, float hi) {
   return r;
 }
 
+// 0xFFFF in each half-word of the result where the corresponding fp16 of `w` is > 0 (one HSET2 per pair)
+__device__ __forceinline__ uint32_t half2_pos_mask(uint32_t w) {
+  const __half2 h = *reinterpret_cast<const __half2*>(&w);
+  return __hgt2_mask(h, __half2half2(__ushort_as_half((unsigned short)0)));
+}
+// ReLU sign-bit words: a 32-bit word covers 32 consecutive columns; element e sits at bit (e/2) + 16*(e%2), i.e. the
+// even columns fill the low half-word and the odd ones the high half-word, so one packed fp16 pair updates its two
+// bits with a single LOP3: bits |= half2_pos_mask(pair) & mask_pair_const(i).
+__host__ __device__ constexpr uint32_t mask_pair_const(int i) { return (1u << i) | (1u << (16 + i)); }
+__host__ __device__ constexpr int mask_pos(int e) { return (e >> 1) + 16 * (e & 1); }
+
 // Forward generation: H1 rows of one tile -> swizzled fp16 A operand (the pair matrix never exists anywhere).
 // Warp `q` (0..3) of the warpgroup owns rows [32q, 32q+32).  Lane mapping: 4 rows x 8 sixteen-byte groups per
-// step -> 256-byte coalesced reads of U, conflict-free STS.  M1 sign bits use the permuted layout
+// step -> 256-byte coalesced reads of U, conflict-free STS.  M1 sign bits use a lane-local layout
 // word j = (col % 64) / 8, bit = (col / 64) * 8 + col % 8.
 template <bool SAVE>
 __device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
@@ -174,15 +185,17 @@ __device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char
       const float4 u0 = __ldg(up + kc * 16), u1 = __ldg(up + kc * 16 + 1);
       const float4 v0 = __ldg(vp + kc * 16), v1 = __ldg(vp + kc * 16 + 1);
       const float h[8] = {u0.x + v0.x, u0.y + v0.y, u0.z + v0.z, u0.w + v0.w, u1.x + v1.x, u1.y + v1.y, u1.z + v1.z, u1.w + v1.w};
-      if (SAVE) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bits |= (h[e] > 0.f ? 1u : 0u) << (kc * 8 + e);
-      }
       uint4 o;
       o.x = pack_relu_half2(h[0], h[1]);
       o.y = pack_relu_half2(h[2], h[3]);
       o.z = pack_relu_half2(h[4], h[5]);
       o.w = pack_relu_half2(h[6], h[7]);
+      if (SAVE) {      // M1, lane-local word j: element (kc, e) -> bit kc*4 + e/2 + 16*(e%2)
+        bits |= half2_pos_mask(o.x) & mask_pair_const(kc * 4 + 0);
+        bits |= half2_pos_mask(o.y) & mask_pair_const(kc * 4 + 1);
+        bits |= half2_pos_mask(o.z) & mask_pair_const(kc * 4 + 2);
+        bits |= half2_pos_mask(o.w) & mask_pair_const(kc * 4 + 3);
+      }
       *reinterpret_cast<uint4*>(a_tile + kc * kAChunk + sw128_offset(row, j * 8)) = o;
     }
     if (SAVE) p.masks[((size_t)tile * kTileM + row) * 8 + j] = bits;      // masks[0] = M1
@@ -207,14 +220,14 @@ __device__ __forceinline__ void generate_dz4(const ChainParams& p, int tile, cha
 #pragma unroll 2
   for (int g = 0; g < 8; ++g) {
     const int row = q * 32 + g * 4 + sub;
-    // cols kc*64 + j*8 + e live in word kc*2 + (j >> 2), bits (j & 3)*8 + e
+    // cols kc*64 + j*8 + e live in word kc*2 + (j >> 2) at bit (j & 3)*4 + e/2 + 16*(e%2)
 #pragma unroll
     for (int kc = 0; kc < kNKC; ++kc) {
       const uint32_t word = __ldg(m4 + (size_t)row * 8 + kc * 2 + (j >> 2));
-      const uint32_t byte = (word >> ((j & 3) * 8)) & 0xffu;
+      const uint32_t nib = word >> ((j & 3) * 4);       // bit e/2 (even e) and 16 + e/2 (odd e) of this lane's 8 columns
       float h[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) h[e] = ((byte >> e) & 1u) ? d[kc][e] : 0.f;
+      for (int e = 0; e < 8; ++e) h[e] = ((nib >> mask_pos(e)) & 1u) ? d[kc][e] : 0.f;
       uint4 o;
       o.x = pack_half2(h[0], h[1]);
       o.y = pack_half2(h[2], h[3]);
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
       mbar_init(smem_u32(&bars->peer_full[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bars->a_full[s]), CTA2 ? 256 : 128);     // pair mode: both CTAs' warpgroups arrive at the leader
+      mbar_init(smem_u32(&bars->a_full[s]), CTA2 ? 8 : 128);       // pair mode: one arrival per warp, from both CTAs, at the leader
       mbar_init(smem_u32(&bars->acc_full[s]), 1);
     }
     fence_mbar_init();
@@ -355,7 +368,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
     const uint32_t acc_full = smem_u32(&bars->acc_full[s]);
     const uint32_t bar_id = 1 + s;
     uint32_t acc_phase = 0;
+    uint32_t swz[8];                 // byte offset of this row's k-th 16-byte group inside a swizzled 128x64 chunk
+#pragma unroll
+    for (int k = 0; k < 8; ++k) swz[k] = sw128_offset(row, k * 8);
 
+    // "this slot's A operand is ready": every thread has written + fenced its part.  Single-CTA: 128 local arrivals.
+    // Pair mode: one (remote) arrival per warp at the leader's barrier keeps the cluster traffic small.
+    auto arrive_a_full = [&]() {
+      if (CTA2) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(a_full);
+      } else {
+        mbar_arrive(a_full);
+      }
+    };
     // stream the freshly written operand image of this slot to HBM (one elected thread, bulk async store)
     auto store_image = [&](char* dst) {
       named_bar_sync(bar_id, 128);              // whole image written and fenced by every thread
@@ -379,7 +405,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
       fence_proxy_async_smem();
       if (MODE == kFwdTrain) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile);
       if (MODE == kDgrad) store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + 3) * kATile);
-      if (CTA2) mbar_arrive_cluster(a_full); else mbar_arrive(a_full);
+      arrive_a_full();
 
       for (int layer = 0; layer < kTcLayers; ++layer) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * kG;
@@ -406,17 +432,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
                 const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + g4 * 8 + 4));
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  v[e] = __uint_as_float(r[g4 * 8 + e]) + bb[e];
-                  bits |= (v[e] > 0.f ? 1u : 0u) << (g4 * 8 + e);
-                }
+                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g4 * 8 + e]) + bb[e];
                 uint4 o;
                 o.x = pack_relu_half2(v[0], v[1]);
                 o.y = pack_relu_half2(v[2], v[3]);
                 o.z = pack_relu_half2(v[4], v[5]);
                 o.w = pack_relu_half2(v[6], v[7]);
+                if (SAVE) {
+                  bits |= half2_pos_mask(o.x) & mask_pair_const(g4 * 4 + 0);
+                  bits |= half2_pos_mask(o.y) & mask_pair_const(g4 * 4 + 1);
+                  bits |= half2_pos_mask(o.z) & mask_pair_const(g4 * 4 + 2);
+                  bits |= half2_pos_mask(o.w) & mask_pair_const(g4 * 4 + 3);
+                }
                 const int col = cc * 32 + g4 * 8;
-                *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + sw128_offset(row, col & 63)) = o;
+                *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + swz[(col >> 3) & 7]) = o;
               }
               mw[cc] = bits;
             }
@@ -427,7 +456,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
             fence_proxy_async_smem();
             if (SAVE) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + layer + 1) * kATile);
             tc_fence_before_sync();
-            if (CTA2) mbar_arrive_cluster(a_full); else mbar_arrive(a_full);
+            arrive_a_full();
           } else {
             // last layer: ReLU + pair-sum.  Column sums over this warp's 32 rows by shuffle transpose-reduce.
             float* part = p.xg_part + ((size_t)tile * 4 + q) * kG;
@@ -440,9 +469,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
               float x[32];
               uint32_t bits = 0;
 #pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                x[e] = fmaxf(__uint_as_float(r[e]) + __ldg(bias + cc * 32 + e), 0.f);
-                bits |= (x[e] > 0.f ? 1u : 0u) << e;
+              for (int e = 0; e < 32; ++e) x[e] = fmaxf(__uint_as_float(r[e]) + __ldg(bias + cc * 32 + e), 0.f);
+              if (SAVE) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) bits |= half2_pos_mask(pack_half2(x[2 * i], x[2 * i + 1])) & mask_pair_const(i);
               }
               mw[cc] = bits;
               part[cc * 32 + lane] = warp_transpose_sum(x, lane);     // lane L holds the sum of column cc*32 + L
@@ -472,9 +502,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
             float x[32];
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              // Z2..Z4 masks: word cc, bit e.  Z1 mask (l == 1): permuted layout written by generate_h1.
-              const uint32_t bit = (l == 1) ? (mw[(cc & 1) * 4 + (e >> 3)] >> ((cc >> 1) * 8 + (e & 7))) & 1u
-                                            : (mw[cc] >> e) & 1u;
+              // Z2..Z4 masks: word cc, bit mask_pos(e).  Z1 mask (l == 1): lane-local layout of generate_h1:
+              // column c -> word (c % 64) / 8, bit (c / 64) * 4 + (c % 8) / 2 + 16 * (c % 2).
+              const uint32_t bit = (l == 1) ? (mw[(cc & 1) * 4 + (e >> 3)] >> ((cc >> 1) * 4 + mask_pos(e & 7))) & 1u
+                                            : (mw[cc] >> mask_pos(e)) & 1u;
               x[e] = bit ? __uint_as_float(r[e]) : 0.f;
             }
 #pragma unroll
@@ -485,13 +516,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
               o.z = pack_half2(x[g4 * 8 + 4], x[g4 * 8 + 5]);
               o.w = pack_half2(x[g4 * 8 + 6], x[g4 * 8 + 7]);
               const int col = cc * 32 + g4 * 8;
-              *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + sw128_offset(row, col & 63)) = o;
+              *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + swz[(col >> 3) & 7]) = o;
             }
           }
           fence_proxy_async_smem();
           store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + (l - 1)) * kATile);
           tc_fence_before_sync();
-          if (layer < kTcLayers - 1) if (CTA2) mbar_arrive_cluster(a_full); else mbar_arrive(a_full);
+          if (layer < kTcLayers - 1) arrive_a_full();
         }
       }
     }
