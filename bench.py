@@ -303,7 +303,12 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None,
+                         # DRAM bytes of one forward+backward launch pair at B=640 (parity mode), from the committed ncu
+                         # capture profiles/r01_chain_wgrad_ncu_full.txt: chain fwd 4.49 GB + dgrad 5.73 GB + 3 x wgrad
+                         # 2.72 GB.  Far above the ~6 MB algorithmic bytes by design: training streams fp16 tile images
+                         # (H1..H3, dZ1..dZ4) through HBM for the weight-gradient GEMMs.
+                         "traffic": 18.4e9 if (precision == "parity" and B == 640) else None,
                          "kernel": "g-MLP (rn_relation_fwd + rn_relation_bwd launches)",
                          "relation_fwd_ms": fwd_ms, "relation_bwd_ms": bwd_ms,
                          "algorithmic_flop_per_launch_pair": G_FLOP_TRAIN * B, "peak_source": peaks["source"] + " (sustained bf16)"},
