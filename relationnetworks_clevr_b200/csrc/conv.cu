@@ -28,6 +28,15 @@ __device__ __forceinline__ float act_in(float y, const float* __restrict__ aff, 
   return aff ? fmaxf(fmaf(aff[2 * kC + c], y, aff[3 * kC + c]), 0.f) : y;
 }
 
+// BatchNorm backward applied on the fly: dy = k0 * (g - k1 - xhat * k2), g = dA where relu(bn(y)) > 0.
+// `aff` = (mean, rstd, scale, shift) and `coef` = (k0, k1, k2) per channel (bn_bwd_finalize_kernel).
+__device__ __forceinline__ float bn_bwd_dy(float yv, float da, const float* __restrict__ aff, const float* __restrict__ coef,
+                                          int c) {
+  const float g = fmaf(aff[2 * kC + c], yv, aff[3 * kC + c]) > 0.f ? da : 0.f;
+  const float xhat = (yv - aff[c]) * aff[kC + c];
+  return coef[c] * (g - coef[kC + c] - xhat * coef[2 * kC + c]);
+}
+
 // ---- asynchronous staging (LDGSTS): every thread keeps ALL its 4-byte copies of a patch in flight at once,
 // so the L2/HBM round trip is paid once per patch instead of once per element -------------------------------
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src, bool valid) {
@@ -344,7 +353,8 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ y, const float* __
 // ------------------------------------------------------------------------------------------
 template <int CIN>
 __global__ void __launch_bounds__(256)
-conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ dy,
+conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ yout,
+                  const float* __restrict__ dA, const float* __restrict__ aff_out, const float* __restrict__ coef,
                   float* __restrict__ part, int hin, int hout, int tiles_x) {
   constexpr int CC = CIN < kChunk ? CIN : kChunk;
   constexpr int NPART = 5;
@@ -359,14 +369,16 @@ conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff
   const int oh0 = (blockIdx.x / tiles_x) * kTile, ow0 = (blockIdx.x % tiles_x) * kTile;
   const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
   const float* inb = in + (size_t)b * CIN * hin * hin;
-  const float* dyb = dy + (size_t)b * kC * hout * hout;
+  const float* yb_o = yout + (size_t)b * kC * hout * hout;
+  const float* dab = dA + (size_t)b * kC * hout * hout;
   float* out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kC * CIN * 9);
 
 #pragma unroll 8
   for (int idx = tid; idx < kC * kTile * kTile; idx += 256) {
     const int co = idx / (kTile * kTile), p = idx % (kTile * kTile);
     const int oh = oh0 + p / kTile, ow = ow0 + p % kTile;
-    dys[co][p] = (oh < hout && ow < hout) ? dyb[((size_t)co * hout + oh) * hout + ow] : 0.f;
+    const size_t o_ = ((size_t)co * hout + oh) * hout + ow;
+    dys[co][p] = (oh < hout && ow < hout) ? bn_bwd_dy(yb_o[o_], dab[o_], aff_out, coef, co) : 0.f;
   }
   const int pp = tid / 48, cg = (tid % 48) / 8, ci = tid % 8;
   const bool active = pp < NPART && ci < CC;
@@ -425,7 +437,8 @@ static size_t wgrad24_smem_bytes() {
 }
 
 __global__ void __launch_bounds__(256)
-conv_wgrad24_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ dy,
+conv_wgrad24_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ yout,
+                    const float* __restrict__ dA, const float* __restrict__ aff_out, const float* __restrict__ coef,
                     float* __restrict__ part, int hin, int hout, int tiles_x) {
   extern __shared__ __align__(16) float wg_smem[];
   float (*patch)[kPatch][kPatch] = reinterpret_cast<float (*)[kPatch][kPatch]>(wg_smem);       // [8][33][33]
@@ -439,14 +452,16 @@ conv_wgrad24_kernel(const float* __restrict__ in, const float* __restrict__ in_a
   const int oh0 = (blockIdx.x / tiles_x) * kTile, ow0 = (blockIdx.x % tiles_x) * kTile;
   const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
   const float* inb = in + (size_t)b * kC * hin * hin;
-  const float* dyb = dy + (size_t)b * kC * hout * hout;
+  const float* yb_o = yout + (size_t)b * kC * hout * hout;
+  const float* dab = dA + (size_t)b * kC * hout * hout;
   float* out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kC * kC * 9);
 
 #pragma unroll 8
   for (int idx = tid; idx < kC * kTile * kTile; idx += 256) {      // coalesced read, pixel-major store
     const int co = idx / (kTile * kTile), p = idx % (kTile * kTile);
     const int oh = oh0 + p / kTile, ow = ow0 + p % kTile;
-    dys[p][co] = (oh < hout && ow < hout) ? dyb[((size_t)co * hout + oh) * hout + ow] : 0.f;
+    const size_t o_ = ((size_t)co * hout + oh) * hout + ow;
+    dys[p][co] = (oh < hout && ow < hout) ? bn_bwd_dy(yb_o[o_], dab[o_], aff_out, coef, co) : 0.f;
   }
 
   for (int ci0 = 0; ci0 < kC; ci0 += kChunk) {
@@ -510,21 +525,24 @@ conv_wgrad24_kernel(const float* __restrict__ in, const float* __restrict__ in_a
 // grid (tiles, B, 3 ci-chunks), block 256
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-conv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dA, int hin, int hout,
+conv_dgrad_kernel(const float* __restrict__ yout, const float* __restrict__ dAout, const float* __restrict__ aff_out,
+                  const float* __restrict__ coef, const float* __restrict__ w, float* __restrict__ dA, int hin, int hout,
                   int tiles_x) {
   __shared__ float dys[kC][kTile + 1][kTile + 2];
   __shared__ __align__(16) float wsm[kC][kChunk][12];
   const int tid = threadIdx.x, tx = tid % kTile, ty = tid / kTile;
   const int b = blockIdx.y, ci0 = blockIdx.z * kChunk;
   const int q0y = (blockIdx.x / tiles_x) * kTile, q0x = (blockIdx.x % tiles_x) * kTile;   // quad == output coords
-  const float* dyb = dy + (size_t)b * kC * hout * hout;
+  const float* yb_o = yout + (size_t)b * kC * hout * hout;
+  const float* dab = dAout + (size_t)b * kC * hout * hout;
 
 #pragma unroll 8
   for (int idx = tid; idx < kC * (kTile + 1) * (kTile + 1); idx += 256) {
     const int co = idx / ((kTile + 1) * (kTile + 1)), rem = idx % ((kTile + 1) * (kTile + 1));
     const int r = rem / (kTile + 1), c = rem % (kTile + 1);
     const int oh = q0y + r, ow = q0x + c;
-    dys[co][r][c] = (oh < hout && ow < hout) ? dyb[((size_t)co * hout + oh) * hout + ow] : 0.f;
+    const size_t o_ = ((size_t)co * hout + oh) * hout + ow;
+    dys[co][r][c] = (oh < hout && ow < hout) ? bn_bwd_dy(yb_o[o_], dab[o_], aff_out, coef, co) : 0.f;
   }
   for (int idx = tid; idx < kC * kChunk * 9; idx += 256) {
     const int co = idx / (kChunk * 9), rem = idx % (kChunk * 9);
@@ -676,8 +694,8 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float
   ConvPlan p = make_plan(*cfg);
   const size_t big = round_up((size_t)cfg->B * kC * p.h[1] * p.h[1], 64);
   float* dA = scratch;
-  float* dy = scratch + big;
-  float* bnpart = dy + big;
+  float* dA_next = scratch + big;      // BatchNorm backward is applied on the fly by the consumers: no dy buffer
+  float* bnpart = dA_next + big;
   size_t spart = 0;
   for (int l = 0; l < RN_CONV_LAYERS; ++l) spart = std::max(spart, (size_t)cfg->B * p.tiles[l] * 2 * kC);
   float* coef = bnpart + round_up(std::max(spart, (size_t)cfg->B * kC * 2), 64);
@@ -702,9 +720,6 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float
     bn_bwd_finalize_kernel<<<1, 32 * kC, 0, st>>>(bnpart, cfg->B, (double)cfg->B * hw, L[l].gamma, aff, coef, Gr[l].dgamma,
                                                  Gr[l].dbeta, Gr[l].dbias, cfg->training);
     RN_LAUNCH_CHECK("bn_bwd_finalize_kernel");
-    const long long total = (long long)cfg->B * kC * hw;
-    bn_bwd_apply_kernel<<<cdiv(total, 256), 256, 0, st>>>(y, dA, aff, coef, dy, hw, total);
-    RN_LAUNCH_CHECK("bn_bwd_apply_kernel");
     // weight gradient: per-block partials, then a fixed-order sum over blocks
     const float* in = l == 0 ? img : saved + p.y_off[l - 1];
     const float* in_aff = l == 0 ? nullptr : saved + p.aff_off[l - 1];
@@ -713,11 +728,11 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float
     if (l == 0) {
       const size_t smem = wgrad_smem_bytes(3);
       RN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conv_wgrad_kernel<3><<<grid, 256, smem, st>>>(in, in_aff, dy, wpart, hin, hout, tx);
+      conv_wgrad_kernel<3><<<grid, 256, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, hin, hout, tx);
     } else {
       const size_t smem = wgrad24_smem_bytes();
       RN_CUDA(cudaFuncSetAttribute(conv_wgrad24_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conv_wgrad24_kernel<<<grid, 256, smem, st>>>(in, in_aff, dy, wpart, hin, hout, tx);
+      conv_wgrad24_kernel<<<grid, 256, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, hin, hout, tx);
     }
     RN_LAUNCH_CHECK("conv_wgrad_kernel");
     {
@@ -740,8 +755,10 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float
     if (l > 0) {
       // data gradient into dA (now sized for layer l-1's output == this layer's input)
       const int qt = cdiv(hout, kTile);
-      conv_dgrad_kernel<<<dim3(qt * qt, cfg->B, kC / kChunk), 256, 0, st>>>(dy, L[l].w, dA, hin, hout, qt);
+      // reads (y_l, dA_l), writes dA_{l-1} into the other buffer
+      conv_dgrad_kernel<<<dim3(qt * qt, cfg->B, kC / kChunk), 256, 0, st>>>(y, dA, aff, coef, L[l].w, dA_next, hin, hout, qt);
       RN_LAUNCH_CHECK("conv_dgrad_kernel");
+      float* t = dA; dA = dA_next; dA_next = t;
     }
   }
   return RN_OK;
