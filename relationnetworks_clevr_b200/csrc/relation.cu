@@ -2,6 +2,8 @@
 // Math: SURVEY.md 7.4 (restating reference model.py:104-152 and its autograd backward).
 #include "relation.cuh"
 
+#include <algorithm>
+
 namespace rn {
 
 // ------------------------------------------------------------------------------------------
@@ -16,9 +18,75 @@ __global__ void add_rowgroup_bias_kernel(float* __restrict__ V, const float* __r
   V[i] += bias[(rows_per_group ? (r / rows_per_group) * group_stride : 0) + c];
 }
 
+// Fused layer-0 "pre" for the from-pixels shapes (k == 26, G <= 256): persistent blocks of G threads (thread = output
+// feature g) keep W0c / W0a rows in registers and the question block transposed in shared memory, and walk the samples:
+//   Qb[b, g] = b_qinj[g] + sum_j q[b, j] Wq[g, j];  U[b, o, g] = x[b, o, :] . W0c[g, :];  Vb = x . W0a[g, :] + beta0
+// One launch instead of three GEMMs and a bias pass; U / Vb rows are written once, fully coalesced.
+template <int K>
+__global__ void __launch_bounds__(256)
+rel_pre_fused_kernel(const float* __restrict__ x, const float* __restrict__ q, const float* __restrict__ w0, int fan0,
+                     const float* __restrict__ wq, int ldq, const float* __restrict__ bq, const float* __restrict__ b0,
+                     int q_at_layer0, int B, int n, int Q, int G, float* __restrict__ U, float* __restrict__ Vb,
+                     float* __restrict__ Qb) {
+  extern __shared__ __align__(16) float pre_smem[];
+  float* wqT = pre_smem;                          // [Q][G + 1]
+  float* xs = wqT + (size_t)Q * (G + 1);          // [n][K]
+  float* qs = xs + (((size_t)n * K + 3) & ~(size_t)3);
+  const int g = threadIdx.x;
+  for (int idx = threadIdx.x; idx < G * Q; idx += blockDim.x) {
+    const int gg = idx / Q, j = idx % Q;
+    wqT[(size_t)j * (G + 1) + gg] = wq[(size_t)gg * ldq + j];
+  }
+  float wc[K], wa[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    wc[j] = w0[(size_t)g * fan0 + j];
+    wa[j] = w0[(size_t)g * fan0 + K + j];
+  }
+  const float bqv = bq[g], b0v = b0[g];
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();            // previous sample's xs / qs are no longer read (also orders the wqT fill)
+    for (int i = threadIdx.x; i < n * K; i += blockDim.x) xs[i] = x[(size_t)b * n * K + i];
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) qs[i] = q[(size_t)b * Q + i];
+    __syncthreads();
+    float acc = bqv;
+#pragma unroll 8
+    for (int j = 0; j < Q; ++j) acc = fmaf(qs[j], wqT[(size_t)j * (G + 1) + g], acc);
+    Qb[(size_t)b * G + g] = acc;
+    const float vb = q_at_layer0 ? acc : b0v;
+    for (int o = 0; o < n; ++o) {
+      float u = 0.f, v = vb;
+#pragma unroll
+      for (int j = 0; j < K; j += 2) {
+        const float2 xv = *reinterpret_cast<const float2*>(&xs[o * K + j]);
+        u = fmaf(xv.x, wc[j], u);
+        u = fmaf(xv.y, wc[j + 1], u);
+        v = fmaf(xv.x, wa[j], v);
+        v = fmaf(xv.y, wa[j + 1], v);
+      }
+      U[((size_t)b * n + o) * G + g] = u;
+      Vb[((size_t)b * n + o) * G + g] = v;
+    }
+  }
+}
+
+static size_t rel_pre_fused_smem(const RelShape& s) {
+  return ((size_t)s.Q * (s.G + 1) + (((size_t)s.n * s.k + 3) & ~(size_t)3) + s.Q) * sizeof(float);
+}
+
 int relation_pre(const RelShape& s, const float* x, const float* q, const float* const* g_w, const float* const* g_b,
                  const RelPre& pre, cudaStream_t st) {
   const int fan0 = s.fan_in(0);
+  if (s.k == 26 && s.G == 256 && rel_pre_fused_smem(s) <= 200 * 1024) {
+    const float* wq = g_w[s.qinj] + (s.qinj == 0 ? 2 * s.k : s.G);
+    const size_t smem = rel_pre_fused_smem(s);
+    RN_CUDA(cudaFuncSetAttribute(rel_pre_fused_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rel_pre_fused_kernel<26><<<std::min(s.B, sm_count()), s.G, smem, st>>>(x, q, g_w[0], fan0, wq, s.fan_in(s.qinj),
+                                                                          g_b[s.qinj], g_b[0], s.qinj == 0 ? 1 : 0, s.B,
+                                                                          s.n, s.Q, s.G, pre.U, pre.Vb, pre.Qb);
+    RN_LAUNCH_CHECK("rel_pre_fused_kernel");
+    return RN_OK;
+  }
   GemmEpilogue none;
   // U[b,c,:] = x[b,c,:] . W0[:, 0:k]^T ; V[b,a,:] = x[b,a,:] . W0[:, k:2k]^T
   RN_TRY(sgemm(false, true, s.B * s.n, s.G, s.k, x, s.k, g_w[0], fan0, pre.U, s.G, none, st));

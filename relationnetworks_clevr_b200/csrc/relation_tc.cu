@@ -113,6 +113,7 @@ struct ChainParams {
   const float* dxg;                // [B, 256]
   const float* scale;              // [0] = S (power of two applied to dxg), [1] = 1/S
   __half* dZ;                      // [tiles][4] x 64 KB images dZ1..dZ4 (scaled by S)
+  int dbg;                         // timing ablations (RN_B200_DBG; results are garbage when nonzero)
 };
 
 struct Bars {
@@ -202,6 +203,65 @@ __device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char
   }
 }
 
+// n == 64 fast path (the 8x8 grid): a tile is 2 values of `a` x all 64 values of `c`, so U[c] is read ONCE for both
+// rows (c, a0) and (c, a1) and the two Vb rows live in registers: 66 KB of L2 reads per tile instead of 256 KB (the
+// chain kernels are bound by L2 -> SM bandwidth).  Warp q takes c in [16q, 16q+16); lane owns columns
+// [4*lane, 4*lane+4) and [128 + 4*lane, 128 + 4*lane + 4): fully coalesced 512-byte U reads, conflict-free STS.64.
+// M1 sign bits by warp ballot: word (half*4 + e) of a row holds columns half*128 + 4*j + e at bit j (j = 0..31).
+template <bool SAVE>
+__device__ __forceinline__ void generate_h1_n64(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
+  const int b = tile / p.tiles_per_sample;
+  const int a0 = (tile % p.tiles_per_sample) * 2;
+  const float* Ub = p.U + (size_t)b * 64 * kG + 4 * lane;
+  const float* Vb = p.Vb + ((size_t)b * 64 + a0) * kG + 4 * lane;
+  float4 v[2][2];
+#pragma unroll
+  for (int ai = 0; ai < 2; ++ai)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) v[ai][h] = __ldg(reinterpret_cast<const float4*>(Vb + ai * kG + h * 128));
+  char* dst0 = a_tile + (lane >> 4) * kAChunk + ((4 * lane) & 7) * 2;       // + row part + swizzled group
+  const int grp = ((4 * lane) & 63) >> 3;
+#pragma unroll 1
+  for (int it = 0; it < 16; it += 4) {
+    float4 u[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = q * 16 + it + i;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) u[i][h] = __ldg(reinterpret_cast<const float4*>(Ub + (size_t)c * kG + h * 128));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = q * 16 + it + i;
+      uint32_t mine = 0;
+#pragma unroll
+      for (int ai = 0; ai < 2; ++ai) {
+        const int row = ai * 64 + c;
+        const uint32_t off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((grp ^ (row & 7)) & 7) << 4));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float h0 = u[i][h].x + v[ai][h].x, h1 = u[i][h].y + v[ai][h].y;
+          const float h2 = u[i][h].z + v[ai][h].z, h3 = u[i][h].w + v[ai][h].w;
+          uint2 o;
+          o.x = pack_relu_half2(h0, h1);
+          o.y = pack_relu_half2(h2, h3);
+          *reinterpret_cast<uint2*>(dst0 + h * 2 * kAChunk + off) = o;
+          if (SAVE) {
+            const uint32_t w0 = __ballot_sync(0xffffffffu, h0 > 0.f), w1 = __ballot_sync(0xffffffffu, h1 > 0.f);
+            const uint32_t w2 = __ballot_sync(0xffffffffu, h2 > 0.f), w3 = __ballot_sync(0xffffffffu, h3 > 0.f);
+            const int base = ai * 8 + h * 4;
+            if (lane == base + 0) mine = w0;
+            if (lane == base + 1) mine = w1;
+            if (lane == base + 2) mine = w2;
+            if (lane == base + 3) mine = w3;
+          }
+        }
+      }
+      if (SAVE && lane < 16) p.masks[((size_t)tile * kTileM + (lane >> 3) * 64 + c) * 8 + (lane & 7)] = mine;   // masks[0] = M1
+    }
+  }
+}
+
 // Backward generation: dZ4[r, :] = S * dxg[b, :] where Z4[r, :] > 0 -> swizzled fp16 A operand.
 // Same lane mapping as generate_h1.  (Column sums of the dZ images are taken by the weight-gradient kernel.)
 __device__ __forceinline__ void generate_dz4(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
@@ -238,10 +298,45 @@ __device__ __forceinline__ void generate_dz4(const ChainParams& p, int tile, cha
   }
 }
 
+// Data-gradient epilogue of one tile row: dZ[row, :] = accumulator[row, :] where the ReLU sign bit is set, as fp16 into
+// the swizzled A operand.  LAYOUT 0: word cc, bit mask_pos(e);  1: M1 of generate_h1;  2: M1 of generate_h1_n64
+// (column c -> word (c / 128) * 4 + c % 4, bit (c % 128) / 4).
+template <int LAYOUT>
+__device__ __forceinline__ void dgrad_mask_tile(uint32_t taddr, const uint32_t (&mw)[8], char* a_tile, const uint32_t (&swz)[8]) {
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) {
+    uint32_t r[32];
+    tmem_ld32(taddr + cc * 32, r);
+    tmem_ld_wait();
+    float x[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const uint32_t bit = LAYOUT == 0   ? (mw[cc] >> mask_pos(e)) & 1u
+                           : LAYOUT == 1 ? (mw[(cc & 1) * 4 + (e >> 3)] >> ((cc >> 1) * 4 + mask_pos(e & 7))) & 1u
+                                         : (mw[(cc >> 2) * 4 + (e & 3)] >> ((cc & 3) * 8 + (e >> 2))) & 1u;
+      x[e] = bit ? __uint_as_float(r[e]) : 0.f;
+    }
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+      uint4 o;
+      o.x = pack_half2(x[g4 * 8 + 0], x[g4 * 8 + 1]);
+      o.y = pack_half2(x[g4 * 8 + 2], x[g4 * 8 + 3]);
+      o.z = pack_half2(x[g4 * 8 + 4], x[g4 * 8 + 5]);
+      o.w = pack_half2(x[g4 * 8 + 6], x[g4 * 8 + 7]);
+      const int col = cc * 32 + g4 * 8;
+      *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + swz[(col >> 3) & 7]) = o;
+    }
+  }
+}
+
 // CTA2 = true: the kernel runs as clusters of two CTAs on one TPC (cta_group::2).  Each CTA keeps its own tile
 // slots, A buffers, epilogue warps and TMEM accumulators, but ONE tcgen05.mma (M = 256) issued by the leader CTA
 // drives both tiles, and each CTA stages only its N-half of every weight chunk: half the L2->smem weight traffic
 // and half the shared-memory operand reads per SM -- the 1-CTA form is shared-memory-bandwidth bound.
+__device__ long long g_chain_prof[160][16];
+#define PROF_T0() long long _t0 = 0; if (prof) _t0 = clock64();
+#define PROF_ACC(i) if (prof) { const long long _t1 = clock64(); pacc[i] += _t1 - _t0; _t0 = _t1; }
+
 template <int MODE, bool CTA2>
 __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainParams p) {
   constexpr bool SAVE = MODE != kFwdEval;        // training forward and dgrad stream operand images to HBM
@@ -290,7 +385,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
         for (int layer = 0; layer < kTcLayers; ++layer) {
           const int img_layer = MODE == kDgrad ? kTcLayers - 1 - layer : layer;    // dgrad walks W3^T, W2^T, W1^T
           for (int s = 0; s < nslots; ++s)
-            for (int pass = 0; pass < p.passes; ++pass)
+            for (int pass = 0; pass < ((p.dbg & 4) ? 0 : (p.dbg & 1) ? 1 : p.passes); ++pass)
               for (int kc = 0; kc < kNKC; ++kc) {
                 mbar_wait(smem_u32(&bars->w_empty[stage]), phase ^ 1);
                 const uint32_t full = smem_u32(&bars->w_full[stage]);
@@ -309,6 +404,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
       // ================= MMA issuer (pair mode: leader CTA only) =================
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
+      const bool prof = (p.dbg & 8) != 0;
+      long long pacc[4] = {0, 0, 0, 0};
+      PROF_T0();
       for (int r = 0; 2 * r < my_tiles; ++r) {
         const int nslots = (2 * r + 1 < my_tiles) ? 2 : 1;
         for (int layer = 0; layer < kTcLayers; ++layer)
@@ -316,16 +414,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
             if (CTA2) mbar_wait_cluster(smem_u32(&bars->a_full[s]), a_phase[s]);
             else mbar_wait(smem_u32(&bars->a_full[s]), a_phase[s]);
             a_phase[s] ^= 1;
+            PROF_ACC(0);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + s * kG;
             const uint32_t a_base = smem_u32(smem + kSmemA + s * kATile);
             uint32_t accumulate = 0;
-            for (int pass = 0; pass < p.passes; ++pass)
+            const int reps = (p.dbg & 1) ? p.passes : 1;
+            for (int pass = 0; pass < ((p.dbg & 1) ? 1 : p.passes); ++pass)
               for (int kc = 0; kc < kNKC; ++kc) {
-                mbar_wait(smem_u32(&bars->w_full[stage]), phase);
+                if (!(p.dbg & 4)) mbar_wait(smem_u32(&bars->w_full[stage]), phase);
                 if (CTA2) mbar_wait_cluster(smem_u32(&bars->peer_full[stage]), phase);
+                PROF_ACC(1);
                 tc_fence_after_sync();
                 const uint32_t b_base = smem_u32(smem + kSmemW + stage * STAGE_BYTES);
+                for (int rep = 0; rep < reps; ++rep)
 #pragma unroll
                 for (int k = 0; k < kKC / 16; ++k) {
                   const uint64_t ad = smem_desc_sw128(a_base + kc * kAChunk + k * 32, 16, 1024);
@@ -336,14 +438,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
                 }
                 // ring stage free (in both CTAs) once these MMAs retire
                 if (CTA2) mma_commit_2cta(smem_u32(&bars->w_empty[stage]), 3);
-                else mma_commit(smem_u32(&bars->w_empty[stage]));
-                if (++stage == NST) { stage = 0; phase ^= 1; }
+                else if (!(p.dbg & 4)) mma_commit(smem_u32(&bars->w_empty[stage]));
+                if (!(p.dbg & 4) && ++stage == NST) { stage = 0; phase ^= 1; }
               }
             // accumulator of (slot, layer) complete (in both CTAs)
             if (CTA2) mma_commit_2cta(smem_u32(&bars->acc_full[s]), 3);
             else mma_commit(smem_u32(&bars->acc_full[s]));
+            PROF_ACC(2);
           }
       }
+      if (prof) for (int i = 0; i < 3; ++i) g_chain_prof[blockIdx.x][8 + i] = pacc[i];
     } else if (CTA2 && lane == 0) {
       // ================= peer CTA relay: tell the leader when this CTA's half of each chunk has landed =================
       uint32_t stage = 0, phase = 0;
@@ -396,16 +500,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
       named_bar_sync(bar_id, 128);
     };
 
+    const bool prof = (p.dbg & 8) != 0 && threadIdx.x == 128;
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+    PROF_T0();
     for (int i = s; i < my_tiles; i += 2) {
       const int tile = tile_first + i * tile_step;
       const int b = tile / p.tiles_per_sample;
+      if (prof) _t0 = clock64();
       if (SAVE) wait_image_read();
       if (MODE == kDgrad) generate_dz4(p, tile, a_tile, q, lane);
+      else if (p.n == 64) generate_h1_n64<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
       else generate_h1<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
       fence_proxy_async_smem();
       if (MODE == kFwdTrain) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile);
       if (MODE == kDgrad) store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + 3) * kATile);
       arrive_a_full();
+      PROF_ACC(0);
 
       for (int layer = 0; layer < kTcLayers; ++layer) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * kG;
@@ -415,10 +526,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
           uint32_t* mrow = SAVE ? p.masks + (((size_t)(layer + 1) * p.num_tiles + tile) * kTileM + row) * 8 : nullptr;
           mbar_wait(acc_full, acc_phase);
           acc_phase ^= 1;
+          PROF_ACC(1);
           tc_fence_after_sync();
           if (layer < kTcLayers - 1) {
             if (SAVE) wait_image_read();
             uint32_t mw[8];
+            if (p.dbg & 2) {
+#pragma unroll
+              for (int cc = 0; cc < 8; ++cc) mw[cc] = 0;
+            } else
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
               uint32_t r[32];
@@ -457,6 +573,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
             if (SAVE) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + layer + 1) * kATile);
             tc_fence_before_sync();
             arrive_a_full();
+            PROF_ACC(2);
           } else {
             // last layer: ReLU + pair-sum.  Column sums over this warp's 32 rows by shuffle transpose-reduce.
             float* part = p.xg_part + ((size_t)tile * 4 + q) * kG;
@@ -482,6 +599,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
               *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
             }
             tc_fence_before_sync();
+            PROF_ACC(3);
           }
         } else {
           // ---------------- data-gradient epilogue: dZ_l = dH_l .* (Z_l > 0), l = 3 - layer ----------------
@@ -492,41 +610,30 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
           const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
           mbar_wait(acc_full, acc_phase);
           acc_phase ^= 1;
+          PROF_ACC(1);
           tc_fence_after_sync();
           wait_image_read();
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            uint32_t r[32];
-            tmem_ld32(taddr + cc * 32, r);
-            tmem_ld_wait();
-            float x[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              // Z2..Z4 masks: word cc, bit mask_pos(e).  Z1 mask (l == 1): lane-local layout of generate_h1:
-              // column c -> word (c % 64) / 8, bit (c / 64) * 4 + (c % 8) / 2 + 16 * (c % 2).
-              const uint32_t bit = (l == 1) ? (mw[(cc & 1) * 4 + (e >> 3)] >> ((cc >> 1) * 4 + mask_pos(e & 7))) & 1u
-                                            : (mw[cc] >> mask_pos(e)) & 1u;
-              x[e] = bit ? __uint_as_float(r[e]) : 0.f;
-            }
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              uint4 o;
-              o.x = pack_half2(x[g4 * 8 + 0], x[g4 * 8 + 1]);
-              o.y = pack_half2(x[g4 * 8 + 2], x[g4 * 8 + 3]);
-              o.z = pack_half2(x[g4 * 8 + 4], x[g4 * 8 + 5]);
-              o.w = pack_half2(x[g4 * 8 + 6], x[g4 * 8 + 7]);
-              const int col = cc * 32 + g4 * 8;
-              *reinterpret_cast<uint4*>(a_tile + (col >> 6) * kAChunk + swz[(col >> 3) & 7]) = o;
-            }
+          if (!(p.dbg & 2)) {
+            // Z2..Z4 masks: word cc, bit mask_pos(e).  Z1 mask: lane-local layout of generate_h1 (column c -> word
+            // (c % 64) / 8, bit (c / 64) * 4 + (c % 8) / 2 + 16 * (c % 2)) or the ballot layout of generate_h1_n64.
+            if (l != 1) dgrad_mask_tile<0>(taddr, mw, a_tile, swz);
+            else if (p.n == 64) dgrad_mask_tile<2>(taddr, mw, a_tile, swz);
+            else dgrad_mask_tile<1>(taddr, mw, a_tile, swz);
           }
           fence_proxy_async_smem();
           store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + (l - 1)) * kATile);
           tc_fence_before_sync();
           if (layer < kTcLayers - 1) arrive_a_full();
+          PROF_ACC(2);
         }
       }
     }
     if (SAVE && wg_tid == 0) bulk_wait0();
+    if (prof) {
+      for (int i = 0; i < 4; ++i) g_chain_prof[blockIdx.x][i] = pacc[i];
+      g_chain_prof[blockIdx.x][4] = clock64() - t_begin;
+      g_chain_prof[blockIdx.x][5] = my_tiles;
+    }
   }
 
   tc_fence_before_sync();
@@ -698,16 +805,25 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int npart
   dW[(size_t)(idx / kG) * ld + idx % kG] = v * scale[1];
 }
 
-// S = 2^k with max|dxg| * S in (4, 8]: keeps the fp16 gradient operands in the normal range
-__global__ void grad_scale_kernel(const float* __restrict__ dxg, int n, float* __restrict__ scale) {
-  __shared__ float red[32];
+// S = 2^k with max|dxg| * S in (4, 8]: keeps the fp16 gradient operands in the normal range.
+// Two stages (per-block maxima, then one block) so the scan is not a single block's chain of L2 round trips.
+__global__ void __launch_bounds__(256) grad_absmax_kernel(const float* __restrict__ dxg, int n, float* __restrict__ part) {
+  __shared__ float red[8];
   float m = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(dxg[i]));
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) m = fmaxf(m, fabsf(dxg[i]));
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    part[blockIdx.x] = m;
+  }
+}
+__global__ void grad_scale_kernel(const float* __restrict__ part, int nparts, float* __restrict__ scale) {
+  float m = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 32) m = fmaxf(m, part[i]);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (threadIdx.x == 0) {
     float S = 1.f;
     if (m > 0.f && isfinite(m)) S = exp2f(3.f - ceilf(log2f(m)));
     scale[0] = S;
@@ -753,6 +869,82 @@ dz1_reduce_kernel(const char* __restrict__ dZ, size_t tile_stride, float* __rest
   }
 }
 
+// n == 64: single pass over the dZ1 images (the generic kernel above reads them twice).  Block (b, kc) walks the 32
+// tiles of sample b; chunk kc of each tile image (128 rows x 64 columns, 16 KB, contiguous) is staged by the TMA
+// engine through a 4-deep ring.  A tile is (a0, a1) x all 64 c:
+//   dU: thread (c = tid / 4, part = tid % 4) adds rows c and 64 + c of its 16 columns into registers over all tiles;
+//   dV: warps 0 / 1 take the column sums of rows [0, 64) / [64, 128) (lane = column pair) and write dV[a] per tile.
+constexpr int kDz1Stages = 4;
+__global__ void __launch_bounds__(256)
+dz1_reduce_n64_kernel(const char* __restrict__ dZ, size_t tile_stride, float* __restrict__ dU, float* __restrict__ dV,
+                      const float* __restrict__ scale) {
+  extern __shared__ __align__(128) char dz1_smem[];
+  char (*stage)[kAChunk] = reinterpret_cast<char (*)[kAChunk]>(dz1_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(dz1_smem + kDz1Stages * kAChunk);
+  const int b = blockIdx.x, kc = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kTiles = 32;
+  const char* src = dZ + (size_t)b * kTiles * tile_stride + (size_t)kc * kAChunk;
+  if (tid == 0) {
+    for (int s = 0; s < kDz1Stages; ++s) mbar_init(smem_u32(&full[s]), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int t = 0; t < kDz1Stages; ++t) {
+      mbar_expect_tx(smem_u32(&full[t]), kAChunk);
+      bulk_g2s(smem_u32(stage[t]), src + (size_t)t * tile_stride, kAChunk, smem_u32(&full[t]));
+    }
+  }
+  const float inv = scale[1];
+  const int c = tid >> 2, part = tid & 3;
+  float au[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) au[e] = 0.f;
+  for (int t = 0; t < kTiles; ++t) {
+    const int s = t % kDz1Stages;
+    mbar_wait(smem_u32(&full[s]), (t / kDz1Stages) & 1);
+    const char* st = stage[s];
+#pragma unroll
+    for (int ai = 0; ai < 2; ++ai) {
+      const int row = ai * 64 + c;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int g = part * 2 + i;
+        const uint4 v = *reinterpret_cast<const uint4*>(st + (row >> 3) * 1024 + (row & 7) * 128 + ((g ^ (row & 7)) << 4));
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          au[i * 8 + 2 * e] += f.x;
+          au[i * 8 + 2 * e + 1] += f.y;
+        }
+      }
+    }
+    if (warp < 2) {            // dV[a = 2t + warp][kc*64 + 2*lane, +1] = sum over the 64 rows of this half
+      float2 acc = make_float2(0.f, 0.f);
+      const uint32_t coff = (uint32_t)(lane & 3) * 4u, grp = (uint32_t)(lane >> 2);
+#pragma unroll 8
+      for (int r = 0; r < 64; ++r) {
+        const int row = warp * 64 + r;
+        const __half2 h = *reinterpret_cast<const __half2*>(st + (row >> 3) * 1024 + (row & 7) * 128 + ((grp ^ (uint32_t)(row & 7)) << 4) + coff);
+        const float2 f = __half22float2(h);
+        acc.x += f.x;
+        acc.y += f.y;
+      }
+      *reinterpret_cast<float2*>(dV + ((size_t)b * 64 + 2 * t + warp) * kG + kc * 64 + 2 * lane) = make_float2(acc.x * inv, acc.y * inv);
+    }
+    __syncthreads();           // everyone is done with this stage
+    if (tid == 0 && t + kDz1Stages < kTiles) {
+      mbar_expect_tx(smem_u32(&full[s]), kAChunk);
+      bulk_g2s(smem_u32(stage[s]), src + (size_t)(t + kDz1Stages) * tile_stride, kAChunk, smem_u32(&full[s]));
+    }
+  }
+  float* dst = dU + ((size_t)b * 64 + c) * kG + kc * 64 + part * 16;
+#pragma unroll
+  for (int e = 0; e < 16; e += 4)
+    *reinterpret_cast<float4*>(dst + e) = make_float4(au[e] * inv, au[e + 1] * inv, au[e + 2] * inv, au[e + 3] * inv);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -789,6 +981,8 @@ size_t tc_saved_bytes(const RelShape& s, bool training) {
   return b;
 }
 
+constexpr int kScaleParts = 254;
+
 struct TcBwdScratch {
   float* scale;
   __half* wpackT;
@@ -804,7 +998,7 @@ static TcBwdScratch tc_carve_bwd(const RelShape& s, void* scratch) {
   Carver c(scratch);
   TcBwdScratch o;
   const size_t tiles = s.rows / kTileM;
-  o.scale = c.take<float>(64);
+  o.scale = c.take<float>(2 + kScaleParts);       // S, 1/S, per-block |dxg| maxima
   o.wpackT = reinterpret_cast<__half*>(c.take<char>(wpack_bytes()));
   o.dZ = reinterpret_cast<__half*>(c.take<char>(tiles * 4 * kATile));
   o.colpart = c.take<float>(tiles * 3 * kG);
@@ -819,7 +1013,7 @@ size_t tc_scratch_bytes(const RelShape& s, bool training) {
   const size_t tiles = s.rows / kTileM;
   const size_t fwd = round_up(tiles * 4 * kG * 4, 256);
   if (!training) return fwd;
-  size_t bwd = 256 + round_up(wpack_bytes(), 256) + round_up(tiles * 4 * kATile, 256) + round_up(tiles * 3 * kG * 4, 256) +
+  size_t bwd = round_up((2 + kScaleParts) * 4, 256) + round_up(wpack_bytes(), 256) + round_up(tiles * 4 * kATile, 256) + round_up(tiles * 3 * kG * 4, 256) +
                round_up((size_t)256 * kG * kG * 4, 256) + round_up((size_t)3 * s.B * kG * 4, 256) +
                2 * round_up((size_t)s.B * s.n * kG * 4, 256);
   return fwd > bwd ? fwd : bwd;
@@ -830,6 +1024,16 @@ static void fill_pack_args(const RelShape& s, const float* const* g_w, PackArgs&
     pa.w[l] = g_w[l + 1];
     pa.ld[l] = s.fan_in(l + 1);
   }
+}
+
+}  // namespace rn
+extern "C" int rn_debug_chain_profile(long long* out) {   // 160 x 16 counters of the last chain launch (RN_B200_DBG & 8)
+  return cudaMemcpyFromSymbol(out, rn::g_chain_prof, sizeof(rn::g_chain_prof)) == cudaSuccess ? 0 : 1;
+}
+namespace rn {
+static int chain_dbg() {
+  static const int v = []() { const char* e = getenv("RN_B200_DBG"); return e ? atoi(e) : 0; }();
+  return v;
 }
 
 template <int MODE>
@@ -874,6 +1078,7 @@ int tc_relation_fwd(const RelShape& s, int precision, bool training, const float
   RN_LAUNCH_CHECK("pack_weights_kernel");
 
   ChainParams p = {};
+  p.dbg = chain_dbg();
   p.U = sv.pre.U;
   p.Vb = sv.pre.Vb;
   for (int l = 0; l < kTcLayers; ++l) {
@@ -908,8 +1113,13 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
   const int tps = (int)(s.pairs / kTileM);
   const int tiles = (int)(s.rows / kTileM);
 
-  grad_scale_kernel<<<1, 1024, 0, st>>>(dxg, s.B * s.G, ws.scale);
-  RN_LAUNCH_CHECK("grad_scale_kernel");
+  {
+    const int nparts = std::min(kScaleParts, cdiv((long long)s.B * s.G, 256));
+    grad_absmax_kernel<<<nparts, 256, 0, st>>>(dxg, s.B * s.G, ws.scale + 2);
+    RN_LAUNCH_CHECK("grad_absmax_kernel");
+    grad_scale_kernel<<<1, 32, 0, st>>>(ws.scale + 2, nparts, ws.scale);
+    RN_LAUNCH_CHECK("grad_scale_kernel");
+  }
   PackArgs pa;
   fill_pack_args(s, g_w, pa);
   pack_weights_kernel<<<cdiv(kTcLayers * kG * (kG / 8), 256), 256, 0, st>>>(pa, ws.wpackT, 1);
@@ -917,11 +1127,15 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
 
   // data gradient chain: dZ4 -> dZ3 -> dZ2 -> dZ1 (images to HBM), column sums of dZ2..dZ4
   ChainParams p = {};
+  p.dbg = chain_dbg();
   p.wpack = ws.wpackT;
   p.n = s.n;
   p.tiles_per_sample = tps;
   p.num_tiles = tiles;
-  p.passes = precision == RN_PRECISION_FAST ? 1 : 2;
+  // one pass (W_hi only) for the data gradient unless RN_B200_DGRAD_PASSES=2: fp16 weight rounding (2^-12 relative,
+  // independent per weight) is far below the ReLU-mask noise of the fp16-activation network
+  static const int dgrad_passes = []() { const char* e = getenv("RN_B200_DGRAD_PASSES"); return (e && e[0] == '2') ? 2 : 1; }();
+  p.passes = precision == RN_PRECISION_FAST ? 1 : dgrad_passes;
   p.masks = sv.masks;
   p.dxg = dxg;
   p.scale = ws.scale;
@@ -955,8 +1169,15 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
   }
 
   // layer 0: dU / dV from the dZ1 images, then the small fp32 products
-  dz1_reduce_kernel<<<dim3(s.B, kNKC), 256, 0, st>>>(reinterpret_cast<const char*>(ws.dZ), (size_t)4 * kATile, ws.dU,
-                                                      ws.dV, ws.scale, s.n, tps);
+  if (s.n == 64) {
+    constexpr int smem = kDz1Stages * kAChunk + 64;
+    RN_CUDA(cudaFuncSetAttribute(dz1_reduce_n64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dz1_reduce_n64_kernel<<<dim3(s.B, kNKC), 256, smem, st>>>(reinterpret_cast<const char*>(ws.dZ), (size_t)4 * kATile, ws.dU,
+                                                            ws.dV, ws.scale);
+  } else {
+    dz1_reduce_kernel<<<dim3(s.B, kNKC), 256, 0, st>>>(reinterpret_cast<const char*>(ws.dZ), (size_t)4 * kATile, ws.dU,
+                                                        ws.dV, ws.scale, s.n, tps);
+  }
   RN_LAUNCH_CHECK("dz1_reduce_kernel");
   return relation_layer0_bwd(s, x, q, g_w, ws.dU, ws.dV, ws.delta, dx, dq, dg_w, dg_b, ws.partial, (size_t)256 * kG * kG, st);
 }

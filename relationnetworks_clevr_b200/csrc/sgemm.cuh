@@ -2,7 +2,7 @@
 //
 // Used by the RN_PRECISION_FP32 relation path (any shape), the f-MLP head and the small layer-0
 // products of the tcgen05 path.  C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] (+ epilogue).
-// 128x128x16 tiles, 256 threads, 8x8 micro-tiles, register-prefetched smem staging; arbitrary
+// 128x128x16 / 64x64x16 / {128,64}x32x16 tiles, 256 threads, register-prefetched smem staging; arbitrary
 // leading dimensions and sub-matrix offsets (scalar, bounds-checked global loads), optional
 // split-K with a deterministic second-pass reduction.
 #pragma once
@@ -22,46 +22,64 @@ struct GemmEpilogue {
   float beta = 0.f;              // C = v + beta * C_old
 };
 
-constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 16, kGemmThreads = 256;
+constexpr int kGemmBK = 16, kGemmThreads = 256;
 
-template <bool AT, bool BT>
+// Tile shapes: 128x128 (8x8 micro-tiles) for large products; 64x64 (4x4) when the 128x128 grid would leave most of
+// the 148 SMs idle (the f-MLP and other [640, 256]-sized outputs); BN = 32 variants for skinny outputs (N <= 32:
+// the layer-0 products with N = k = 26).  Threads form a 16x16 grid; thread (ty, tx) owns rows ty*4+i (and
+// BM/2 + ty*4 + i when TM == 8) / ty*TM + i otherwise, and the same along N.
+template <int T>
+__device__ __forceinline__ int gemm_frag_index(int t, int i, int B) {
+  return T == 8 ? (i < 4 ? t * 4 + i : B / 2 + t * 4 + (i - 4)) : t * T + i;
+}
+
+template <bool AT, bool BT, int BM, int BN>
 __global__ void __launch_bounds__(kGemmThreads)
 sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long long lda, const float* __restrict__ B,
              long long ldb, float* __restrict__ C, long long ldc, GemmEpilogue ep, int k_chunk,
              long long split_stride) {
-  __shared__ __align__(16) float As[kGemmBK][kGemmBM + 4];
-  __shared__ __align__(16) float Bs[kGemmBK][kGemmBN + 4];
+  constexpr int TM = BM / 16, TN = BN / 16;
+  constexpr int LA = BM * kGemmBK / kGemmThreads, LB = BN * kGemmBK / kGemmThreads;     // staged elements per thread
+  __shared__ __align__(16) float As[kGemmBK][BM + 4];
+  __shared__ __align__(16) float Bs[kGemmBK][BN + 4];
 
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * kGemmBN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int k_begin = blockIdx.z * k_chunk;
   const int k_end = min(K, k_begin + k_chunk);
   const int tx = tid % 16, ty = tid / 16;
 
-  float acc[8][8];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  float ra[8], rb[8];
+  float ra[LA], rb[LB];
 
+  // element i of this thread's share of the A tile: (m, k) inside the tile, contiguous in memory across threads
+  auto a_coord = [&](int i, int& m, int& k) {
+    if (AT) { m = tid % BM; k = tid / BM + (kGemmThreads / BM) * i; }       // memory contiguous along m
+    else    { k = tid % 16; m = tid / 16 + 16 * i; }                        // memory contiguous along k
+  };
+  auto b_coord = [&](int i, int& n, int& k) {
+    if (BT) { k = tid % 16; n = tid / 16 + 16 * i; }                        // B[n*ldb + k]
+    else    { n = tid % BN; k = tid / BN + (kGemmThreads / BN) * i; }       // B[k*ldb + n]
+  };
   auto load_tiles = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < LA; ++i) {
       int m, k;
-      if (AT) { m = tid % 128; k = tid / 128 + 2 * i; }      // memory contiguous along m
-      else    { k = tid % 16;  m = tid / 16 + 16 * i; }      // memory contiguous along k
+      a_coord(i, m, k);
       const int gm = m0 + m, gk = k0 + k;
       float v = 0.f;
       if (gm < M && gk < k_end) v = AT ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
       ra[i] = v;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < LB; ++i) {
       int n, k;
-      if (BT) { k = tid % 16;  n = tid / 16 + 16 * i; }      // B[n*ldb + k]
-      else    { n = tid % 128; k = tid / 128 + 2 * i; }      // B[k*ldb + n]
+      b_coord(i, n, k);
       const int gn = n0 + n, gk = k0 + k;
       float v = 0.f;
       if (gn < N && gk < k_end) v = BT ? B[(long long)gn * ldb + gk] : B[(long long)gk * ldb + gn];
@@ -70,17 +88,15 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long long lda, co
   };
   auto store_tiles = [&]() {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < LA; ++i) {
       int m, k;
-      if (AT) { m = tid % 128; k = tid / 128 + 2 * i; }
-      else    { k = tid % 16;  m = tid / 16 + 16 * i; }
+      a_coord(i, m, k);
       As[k][m] = ra[i];
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < LB; ++i) {
       int n, k;
-      if (BT) { k = tid % 16;  n = tid / 16 + 16 * i; }
-      else    { n = tid % 128; k = tid / 128 + 2 * i; }
+      b_coord(i, n, k);
       Bs[k][n] = rb[i];
     }
   };
@@ -93,15 +109,23 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long long lda, co
       if (k0 + kGemmBK < k_end) load_tiles(k0 + kGemmBK);
 #pragma unroll
       for (int kk = 0; kk < kGemmBK; ++kk) {
-        float a[8], b[8];
-        *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-        *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
-        *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-        *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+        float a[TM], b[TN];
+        if (TM >= 4) {
+          *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+          if (TM == 8) *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[kk][BM / 2 + ty * 4]);
+        } else {
+          *reinterpret_cast<float2*>(&a[0]) = *reinterpret_cast<const float2*>(&As[kk][ty * 2]);
+        }
+        if (TN >= 4) {
+          *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+          if (TN == 8) *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&Bs[kk][BN / 2 + tx * 4]);
+        } else {
+          *reinterpret_cast<float2*>(&b[0]) = *reinterpret_cast<const float2*>(&Bs[kk][tx * 2]);
+        }
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
       }
       __syncthreads();
     }
@@ -110,15 +134,15 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long long lda, co
   float* Cz = C + (long long)blockIdx.z * split_stride;
   const bool raw = split_stride != 0;   // split-K partials: no epilogue here
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + gemm_frag_index<TM>(ty, i, BM);
     if (gm >= M) continue;
     const float* bias_row = nullptr;
     if (!raw && ep.bias)
       bias_row = ep.bias + (ep.bias_group_rows ? (long long)(gm / ep.bias_group_rows) * ep.bias_group_stride : 0);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + gemm_frag_index<TN>(tx, j, BN);
       if (gn >= N) continue;
       float v = acc[i][j];
       if (!raw) {
@@ -149,12 +173,30 @@ static __global__ void splitk_reduce_kernel(int M, int N, int splits, const floa
   C[(long long)gm * ldc + gn] = v;
 }
 
+template <int BM, int BN>
+static void sgemm_launch(bool at, bool bt, dim3 grid, cudaStream_t st, int M, int N, int K, const float* A, long long lda,
+                         const float* B, long long ldb, float* out, long long ld_out, const GemmEpilogue& ep, int k_chunk,
+                         long long split_stride) {
+  if (at && bt) sgemm_kernel<true, true, BM, BN><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+  else if (at) sgemm_kernel<true, false, BM, BN><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+  else if (bt) sgemm_kernel<false, true, BM, BN><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+  else sgemm_kernel<false, false, BM, BN><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+}
+
 // Launch.  `splitk_ws` (floats, >= splits*M*N) enables split-K when K is long and the tile grid small.
 inline int sgemm(bool at, bool bt, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
                  float* C, long long ldc, const GemmEpilogue& ep, cudaStream_t st, float* splitk_ws = nullptr,
                  size_t splitk_ws_floats = 0) {
   if (M <= 0 || N <= 0) return RN_OK;
-  dim3 grid(cdiv(M, kGemmBM), cdiv(N, kGemmBN), 1);
+  // tile choice: skinny outputs get BN = 32; otherwise 128x128 unless that grid cannot fill the machine
+  int bm = 128, bn = 128;
+  if (N <= 32) {
+    bn = 32;
+    bm = (long long)cdiv(M, 128) >= 2LL * sm_count() ? 128 : 64;
+  } else if ((long long)cdiv(M, 128) * cdiv(N, 128) < sm_count()) {
+    bm = bn = 64;
+  }
+  dim3 grid(cdiv(M, bm), cdiv(N, bn), 1);
   int splits = 1;
   const long long tiles = (long long)grid.x * grid.y;
   if (splitk_ws && K >= 2048 && tiles < 2LL * sm_count()) {
@@ -173,10 +215,10 @@ inline int sgemm(bool at, bool bt, int M, int N, int K, const float* A, long lon
     out = splitk_ws;
     ld_out = N;
   }
-  if (at && bt) sgemm_kernel<true, true><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
-  else if (at) sgemm_kernel<true, false><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
-  else if (bt) sgemm_kernel<false, true><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
-  else sgemm_kernel<false, false><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+  if (bm == 128 && bn == 128) sgemm_launch<128, 128>(at, bt, grid, st, M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+  else if (bm == 64 && bn == 64) sgemm_launch<64, 64>(at, bt, grid, st, M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+  else if (bm == 128) sgemm_launch<128, 32>(at, bt, grid, st, M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
+  else sgemm_launch<64, 32>(at, bt, grid, st, M, N, K, A, lda, B, ldb, out, ld_out, ep, k_chunk, split_stride);
   RN_LAUNCH_CHECK("sgemm_kernel");
   if (splits > 1) {
     const long long total = (long long)M * N;
@@ -208,7 +250,9 @@ static __global__ void colsum_kernel(const float* __restrict__ A, float* __restr
   }
 }
 
-// float4 variant for wide rows (N % 4 == 0): block = 64 column groups x 4 row lanes, 1 KB coalesced row segments
+// float4 variant for wide rows (N % 4 == 0): block = 64 column groups x 4 row lanes, 1 KB coalesced row segments;
+// eight independent loads in flight per thread so that tall single-output sums (bias gradients: one output row,
+// hundreds of input rows) are not a chain of exposed L2 round trips.
 static __global__ void __launch_bounds__(256)
 colsum4_kernel(const float* __restrict__ A, float* __restrict__ out, int N, int n2, long long s1, long long s2,
                long long si, int count) {
@@ -221,11 +265,12 @@ colsum4_kernel(const float* __restrict__ A, float* __restrict__ out, int N, int 
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < N) {
     int i = rl;
-    for (; i + 4 < count; i += 8) {       // two independent loads in flight
-      const float4 v0 = *reinterpret_cast<const float4*>(base + i * si * N + col);
-      const float4 v1 = *reinterpret_cast<const float4*>(base + (i + 4) * si * N + col);
-      acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
-      acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+    for (; i + 28 < count; i += 32) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(base + (i + 4 * u) * si * N + col);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
     }
     for (; i < count; i += 4) {
       const float4 v0 = *reinterpret_cast<const float4*>(base + i * si * N + col);
