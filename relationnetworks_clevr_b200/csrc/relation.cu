@@ -33,9 +33,18 @@ rel_pre_fused_kernel(const float* __restrict__ x, const float* __restrict__ q, c
   float* xs = wqT + (size_t)Q * (G + 1);          // [n][K]
   float* qs = xs + (((size_t)n * K + 3) & ~(size_t)3);
   const int g = threadIdx.x;
-  for (int idx = threadIdx.x; idx < G * Q; idx += blockDim.x) {
-    const int gg = idx / Q, j = idx % Q;
-    wqT[(size_t)j * (G + 1) + gg] = wq[(size_t)gg * ldq + j];
+  for (int base = 0; base < G * Q; base += 8 * blockDim.x) {      // 8 loads in flight per thread
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * blockDim.x + threadIdx.x;
+      t[u] = idx < G * Q ? wq[(size_t)(idx / Q) * ldq + idx % Q] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * blockDim.x + threadIdx.x;
+      if (idx < G * Q) wqT[(size_t)(idx % Q) * (G + 1) + idx / Q] = t[u];
+    }
   }
   float wc[K], wa[K];
 #pragma unroll
@@ -46,7 +55,19 @@ rel_pre_fused_kernel(const float* __restrict__ x, const float* __restrict__ q, c
   const float bqv = bq[g], b0v = b0[g];
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();            // previous sample's xs / qs are no longer read (also orders the wqT fill)
-    for (int i = threadIdx.x; i < n * K; i += blockDim.x) xs[i] = x[(size_t)b * n * K + i];
+    for (int base = 0; base < n * K; base += 8 * blockDim.x) {
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * blockDim.x + threadIdx.x;
+        t[u] = i < n * K ? x[(size_t)b * n * K + i] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * blockDim.x + threadIdx.x;
+        if (i < n * K) xs[i] = t[u];
+      }
+    }
     for (int i = threadIdx.x; i < Q; i += blockDim.x) qs[i] = q[(size_t)b * Q + i];
     __syncthreads();
     float acc = bqv;

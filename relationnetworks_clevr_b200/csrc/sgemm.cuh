@@ -287,9 +287,40 @@ colsum4_kernel(const float* __restrict__ A, float* __restrict__ out, int N, int 
   }
 }
 
+// tall single-output sum (bias gradients): out[:] = sum_{i<count} A[i*si, :].  Block = 32 columns x 32 row lanes
+// (1024 threads), so even a 256-column sum spreads over 8 SMs with ~8 K loads in flight each; fixed order.
+static __global__ void __launch_bounds__(1024)
+colsum_tall_kernel(const float* __restrict__ A, float* __restrict__ out, int N, long long si, int count) {
+  __shared__ float red[32][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (col < N) {
+    int i = threadIdx.y;
+    for (; i + 96 < count; i += 128) {
+      const float v0 = A[(long long)i * si * N + col], v1 = A[(long long)(i + 32) * si * N + col];
+      const float v2 = A[(long long)(i + 64) * si * N + col], v3 = A[(long long)(i + 96) * si * N + col];
+      acc += (v0 + v1) + (v2 + v3);
+    }
+    for (; i < count; i += 32) acc += A[(long long)i * si * N + col];
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float v = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) v += red[y][threadIdx.x];
+    out[col] = v;
+  }
+}
+
 inline int colsum(const float* A, float* out, int N, int n1, int n2, long long s1, long long s2, long long si,
                   int count, cudaStream_t st) {
   if (n1 * n2 <= 0) return RN_OK;
+  if (n1 * n2 == 1 && count >= 64) {
+    colsum_tall_kernel<<<cdiv(N, 32), dim3(32, 32), 0, st>>>(A, out, N, si, count);
+    RN_LAUNCH_CHECK("colsum_tall_kernel");
+    return RN_OK;
+  }
   if (N % 4 == 0 && N >= 64 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
     colsum4_kernel<<<dim3(n1 * n2, cdiv(N, 256)), 256, 0, st>>>(A, out, N, n2, s1, s2, si, count);
     RN_LAUNCH_CHECK("colsum4_kernel");

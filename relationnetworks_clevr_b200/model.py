@@ -174,8 +174,20 @@ class RN(nn.Module):
     def forward(self, img: torch.Tensor, qst_idxs: torch.Tensor):
         if not img.is_cuda:
             raise RuntimeError("RN (B200-native) needs CUDA inputs: call model.cuda() and move the batch to the GPU")
-        x = img if self.state_desc else self.conv.objects(img)
-        qst = self.text(qst_idxs)
+        if self.state_desc or os.environ.get("RN_B200_TEXT_STREAM", "1") == "0":
+            x = img if self.state_desc else self.conv.objects(img)
+            qst = self.text(qst_idxs)
+            return self.rl(x, qst)
+        # The question encoder (PyTorch/cuDNN, a chain of small latency-bound kernels) runs on a side stream next to
+        # the conv stack; autograd replays its backward on the same side stream, next to the conv backward.
+        cur = torch.cuda.current_stream(img.device)
+        side = ops.side_stream(img.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            qst = self.text(qst_idxs)
+        x = self.conv.objects(img)
+        cur.wait_stream(side)
+        qst.record_stream(cur)
         return self.rl(x, qst)
 
     def build_coord_tensor(self, b, d):

@@ -26,6 +26,27 @@ def _scratch_bytes(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
     return buf
 
 
+# ---- side stream for work that overlaps the kernels of this library (model.RN runs the question encoder on it) ----
+_side_streams: Dict[int, torch.cuda.Stream] = {}
+
+
+def side_stream(device: torch.device) -> torch.cuda.Stream:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _side_streams.get(idx)
+    if st is None:
+        st = torch.cuda.Stream(device=idx)
+        _side_streams[idx] = st
+    return st
+
+
+def _mark_for_side_consumers(t: torch.Tensor) -> None:
+    """A gradient produced here may be consumed by a backward node running on the side stream: keep the caching
+    allocator from recycling it before that stream is done with it."""
+    st = _side_streams.get(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    if st is not None:
+        t.record_stream(st)
+
+
 # ---- optional CUDA-event timers around the relation launches (bench.py's roofline leg) ----------
 _timers_on = False
 _timer_events: Dict[str, list] = {}
@@ -141,6 +162,7 @@ class RelationFunction(torch.autograd.Function):
             check(lib().rn_relation_bwd(C.byref(cfg), dxg_.data_ptr(), x_.data_ptr(), q_.data_ptr(), ptr_array(ws),
                                         ctx.saved_buf.data_ptr(), dx.data_ptr(), dq.data_ptr(), ptr_array(dws),
                                         ptr_array(dbs), scratch.data_ptr(), _stream()), "rn_relation_bwd")
+        _mark_for_side_consumers(dq)
         grads = []
         for dw, db in zip(dws, dbs):
             grads += [dw, db]
