@@ -389,174 +389,160 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ y, const float* __
 }
 
 // ------------------------------------------------------------------------------------------
-// weight gradient: per-block partial dW[24][CIN][9] over a 16x16 tile of dy
-// grid (tiles, B), block 256: 240 threads = 5 pixel partitions x 6 co-groups(4) x 8 ci
+// dy staging shared by the weight- and data-gradient kernels: dy = BatchNorm-backward(dA, y) of a
+// [24][ROWS][COLS] window (zero outside the image), one aligned float4 of y and dA per item when the output edge is
+// a multiple of 4 (shift-only index arithmetic), scalars otherwise.  dst row stride LDR, channel stride LDC floats.
 // ------------------------------------------------------------------------------------------
+template <int ROWS, int COLS, int LDR, int LDC>
+__device__ __forceinline__ void stage_dy(float* __restrict__ dst, const float* __restrict__ yb, const float* __restrict__ dab,
+                                         const float* __restrict__ aff, const float* __restrict__ coef, int oh0, int ow0,
+                                         int hout, int tid) {
+  constexpr int NV = COLS / 4, TAIL = COLS % 4;          // vectors per row, scalar tail columns
+  if ((hout & 3) == 0) {
+    constexpr int PER = NV + TAIL;
+    for (int idx = tid; idx < kC * ROWS * PER; idx += 256) {
+      const int co = idx / (ROWS * PER), rem = idx - co * (ROWS * PER);
+      const int r = rem / PER, v = rem - r * PER;
+      const int oh = oh0 + r;
+      const float mean = aff[co], rstd = aff[kC + co], sc = aff[2 * kC + co], sh = aff[3 * kC + co];
+      const float k0 = coef[co], k1 = coef[kC + co], k2 = coef[2 * kC + co];
+      float* d = dst + co * LDC + r * LDR;
+      if (v < NV) {
+        const int ow = ow0 + 4 * v;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (oh < hout && ow < hout) {
+          const size_t o_ = ((size_t)co * hout + oh) * hout + ow;
+          const float4 yv = *reinterpret_cast<const float4*>(yb + o_);
+          const float4 da = *reinterpret_cast<const float4*>(dab + o_);
+          o.x = k0 * ((fmaf(sc, yv.x, sh) > 0.f ? da.x : 0.f) - k1 - (yv.x - mean) * rstd * k2);
+          o.y = k0 * ((fmaf(sc, yv.y, sh) > 0.f ? da.y : 0.f) - k1 - (yv.y - mean) * rstd * k2);
+          o.z = k0 * ((fmaf(sc, yv.z, sh) > 0.f ? da.z : 0.f) - k1 - (yv.z - mean) * rstd * k2);
+          o.w = k0 * ((fmaf(sc, yv.w, sh) > 0.f ? da.w : 0.f) - k1 - (yv.w - mean) * rstd * k2);
+        }
+        *reinterpret_cast<float4*>(d + 4 * v) = o;
+      } else {
+        const int c = 4 * NV + (v - NV), ow = ow0 + c;
+        const size_t o_ = ((size_t)co * hout + oh) * hout + ow;
+        d[c] = (oh < hout && ow < hout) ? bn_bwd_dy(yb[o_], dab[o_], aff, coef, co) : 0.f;
+      }
+    }
+  } else {
+    for (int idx = tid; idx < kC * ROWS * COLS; idx += 256) {
+      const int co = idx / (ROWS * COLS), rem = idx % (ROWS * COLS);
+      const int r = rem / COLS, c = rem % COLS;
+      const int oh = oh0 + r, ow = ow0 + c;
+      const size_t o_ = ((size_t)co * hout + oh) * hout + ow;
+      dst[co * LDC + r * LDR + c] = (oh < hout && ow < hout) ? bn_bwd_dy(yb[o_], dab[o_], aff, coef, co) : 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient: per-block partial dW[24][CIN][9] over a 16x16 tile of dy.  grid (tiles, B), block 256.
+// A thread owns 6 output channels x 9 taps of ONE input channel (54 accumulators): per pixel 9 input LDS + 6 dy
+// LDS (broadcast) feed 54 FFMA.
+//   CIN == 24: warp = pixel partition; lane = 4 output-channel groups x 8 input channels; three 8-channel chunks.
+//   CIN == 3 : warp = TWO pixel partitions; lane = 2 x (4 groups x 3 channels) (24 of 32 lanes busy).
+// Partitions are combined by a fixed-order tree (shuffle between the two sub-partitions, then shared memory).
+// ------------------------------------------------------------------------------------------
+constexpr int kDyLd = kTile * kTile + 4;          // channel stride of the staged dy: 6*260 mod 32 = 24 -> the 4 groups hit distinct banks
+constexpr int kWgRedFloats = 4 * 32 * 54;
+template <int CIN>
+constexpr int wgrad_chunk() { return CIN < kChunk ? CIN : kChunk; }
+template <int CIN>
+static size_t wgrad_smem_bytes() {
+  return ((size_t)wgrad_chunk<CIN>() * kPatch * kPW + (size_t)kC * kDyLd) * sizeof(float) < (size_t)kWgRedFloats * 4 + (size_t)kC * kDyLd * 4
+             ? (size_t)kWgRedFloats * 4 + (size_t)kC * kDyLd * 4
+             : ((size_t)wgrad_chunk<CIN>() * kPatch * kPW + (size_t)kC * kDyLd) * sizeof(float);
+}
+
 template <int CIN>
 __global__ void __launch_bounds__(256)
 conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ yout,
                   const float* __restrict__ dA, const float* __restrict__ aff_out, const float* __restrict__ coef,
                   float* __restrict__ part, int hin, int hout, int tiles_x) {
-  constexpr int CC = CIN < kChunk ? CIN : kChunk;
-  constexpr int NPART = 5;
+  constexpr int CC = wgrad_chunk<CIN>();
+  constexpr int PATCH_FLOATS = CC * kPatch * kPW > kWgRedFloats ? CC * kPatch * kPW : kWgRedFloats;
+  constexpr int NSUB = CIN == 3 ? 2 : 1;             // pixel partitions per warp
   extern __shared__ __align__(16) float wg_smem[];
   float (*patch)[kPatch][kPW] = reinterpret_cast<float (*)[kPatch][kPW]>(wg_smem);
-  float (*dys)[kTile * kTile] = reinterpret_cast<float (*)[kTile * kTile]>(wg_smem + CC * kPatch * kPW);
-  float (*accs)[6][CC][37] =
-      reinterpret_cast<float (*)[6][CC][37]>(wg_smem + CC * kPatch * kPW + kC * kTile * kTile);
+  float* red = wg_smem;                                          // aliases the patch between channel chunks
+  float* dys = wg_smem + PATCH_FLOATS;                           // [24][kDyLd]
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = CIN == 3 ? lane / 12 : 0;
+  const int cg = CIN == 3 ? (lane % 12) / 3 : lane >> 3;
+  const int ci = CIN == 3 ? lane % 3 : lane & 7;
+  const bool lane_active = CIN != 3 || lane < 24;
+  const int pp = warp * NSUB + (lane_active ? sub : 0);
   const int b = blockIdx.y;
   const int oh0 = (blockIdx.x / tiles_x) * kTile, ow0 = (blockIdx.x % tiles_x) * kTile;
   const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
   const float* inb = in + (size_t)b * CIN * hin * hin;
-  const float* yb_o = yout + (size_t)b * kC * hout * hout;
-  const float* dab = dA + (size_t)b * kC * hout * hout;
   float* out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kC * CIN * 9);
 
-#pragma unroll 8
-  for (int idx = tid; idx < kC * kTile * kTile; idx += 256) {
-    const int co = idx / (kTile * kTile), p = idx % (kTile * kTile);
-    const int oh = oh0 + p / kTile, ow = ow0 + p % kTile;
-    const size_t o_ = ((size_t)co * hout + oh) * hout + ow;
-    dys[co][p] = (oh < hout && ow < hout) ? bn_bwd_dy(yb_o[o_], dab[o_], aff_out, coef, co) : 0.f;
-  }
-  const int pp = tid / 48, cg = (tid % 48) / 8, ci = tid % 8;
-  const bool active = pp < NPART && ci < CC;
+  stage_dy<kTile, kTile, kTile, kDyLd>(dys, yout + (size_t)b * kC * hout * hout, dA + (size_t)b * kC * hout * hout, aff_out,
+                                      coef, oh0, ow0, hout, tid);
 
   for (int ci0 = 0; ci0 < CIN; ci0 += CC) {
     __syncthreads();
     stage_patch<CC>(patch, inb, in_aff, ci0, ih0, iw0, hin, tid);
-    __syncthreads();
-    if (active) {
-      float acc[4][9];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
-      for (int p = pp; p < kTile * kTile; p += NPART) {
-        const int py = p / kTile, px = p % kTile;
-        float xv[9];
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) xv[kh * 3 + kw] = patch[ci][2 * py + kh][2 * px + kw + kPO];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float g = dys[cg * 4 + j][p];
-#pragma unroll
-          for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(g, xv[t], acc[j][t]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int t = 0; t < 9; ++t) accs[pp][cg][ci][j * 9 + t] = acc[j][t];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < 6 * CC * 36; idx += 256) {
-      const int g6 = idx / (CC * 36), rem = idx % (CC * 36);
-      const int cc = rem / 36, jt = rem % 36;
-      float v = 0.f;
-#pragma unroll
-      for (int q = 0; q < NPART; ++q) v += accs[q][g6][cc][jt];
-      const int co = g6 * 4 + jt / 9, t = jt % 9;
-      out[((size_t)co * CIN + ci0 + cc) * 9 + t] = v;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// weight gradient, 24 input channels (layers 2..4): per-block partial dW[24][24][9] over a 16x16 tile of dy.
-// grid (tiles, B), block 256 = 8 pixel partitions (one warp each) x 4 output-channel groups (6) x 8 input
-// channels: 54 accumulators per thread; per pixel 3 LDS.64 (dy, pixel-major, broadcast over ci) + 9 input LDS
-// (broadcast over the channel groups) feed 54 FFMA.  Partitions are combined by a 3-round tree in smem.
-// ------------------------------------------------------------------------------------------
-constexpr int kWg2RedFloats = 4 * 32 * 54;
-static size_t wgrad24_smem_bytes() {
-  return ((size_t)kChunk * kPatch * kPW + (size_t)kTile * kTile * kC) * sizeof(float);
-}
-
-__global__ void __launch_bounds__(256)
-conv_wgrad24_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ yout,
-                    const float* __restrict__ dA, const float* __restrict__ aff_out, const float* __restrict__ coef,
-                    float* __restrict__ part, int hin, int hout, int tiles_x) {
-  extern __shared__ __align__(16) float wg_smem[];
-  float (*patch)[kPatch][kPW] = reinterpret_cast<float (*)[kPatch][kPW]>(wg_smem);       // [8][33][33]
-  float* red = wg_smem;                                          // aliases the patch between channel chunks
-  float (*dys)[kC] = reinterpret_cast<float (*)[kC]>(wg_smem + kChunk * kPatch * kPW);      // [256][24]
-  static_assert(kWg2RedFloats <= kChunk * kPatch * kPW, "reduction buffer must fit in the patch");
-
-  const int tid = threadIdx.x, lane = tid & 31, pp = tid >> 5;
-  const int cg = lane >> 3, ci = lane & 7;
-  const int b = blockIdx.y;
-  const int oh0 = (blockIdx.x / tiles_x) * kTile, ow0 = (blockIdx.x % tiles_x) * kTile;
-  const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
-  const float* inb = in + (size_t)b * kC * hin * hin;
-  const float* yb_o = yout + (size_t)b * kC * hout * hout;
-  const float* dab = dA + (size_t)b * kC * hout * hout;
-  float* out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kC * kC * 9);
-
-#pragma unroll 8
-  for (int idx = tid; idx < kC * kTile * kTile; idx += 256) {      // coalesced read, pixel-major store
-    const int co = idx / (kTile * kTile), p = idx % (kTile * kTile);
-    const int oh = oh0 + p / kTile, ow = ow0 + p % kTile;
-    const size_t o_ = ((size_t)co * hout + oh) * hout + ow;
-    dys[p][co] = (oh < hout && ow < hout) ? bn_bwd_dy(yb_o[o_], dab[o_], aff_out, coef, co) : 0.f;
-  }
-
-  for (int ci0 = 0; ci0 < kC; ci0 += kChunk) {
-    __syncthreads();
-    stage_patch<kChunk>(patch, inb, in_aff, ci0, ih0, iw0, hin, tid);
     __syncthreads();
     float acc[6][9];
 #pragma unroll
     for (int j = 0; j < 6; ++j)
 #pragma unroll
       for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
+    if (lane_active) {
 #pragma unroll 2
-    for (int p = pp; p < kTile * kTile; p += 8) {
-      const int py = p / kTile, px = p % kTile;
-      if (oh0 + py >= hout || ow0 + px >= hout) continue;      // dy is zero there (warp-uniform)
-      float xv[9];
+      for (int p = pp; p < kTile * kTile; p += 8 * NSUB) {
+        const int py = p / kTile, px = p % kTile;
+        if (oh0 + py >= hout || ow0 + px >= hout) continue;      // dy is zero there
+        float xv[9];
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
+        for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) xv[kh * 3 + kw] = patch[ci][2 * py + kh][2 * px + kw + kPO];
-      const float2 g0 = *reinterpret_cast<const float2*>(&dys[p][cg * 6]);
-      const float2 g1 = *reinterpret_cast<const float2*>(&dys[p][cg * 6 + 2]);
-      const float2 g2 = *reinterpret_cast<const float2*>(&dys[p][cg * 6 + 4]);
-      const float g[6] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y};
+          for (int kw = 0; kw < 3; ++kw) xv[kh * 3 + kw] = patch[ci][2 * py + kh][2 * px + kw + kPO];
+        float g[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) g[j] = dys[(cg * 6 + j) * kDyLd + p];
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(g[j], xv[t], acc[j][t]);
+      }
+    }
+    if (NSUB == 2) {           // fold sub-partition 1 (lanes 12..23) into sub-partition 0 (lanes 0..11)
 #pragma unroll
       for (int j = 0; j < 6; ++j)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(g[j], xv[t], acc[j][t]);
+        for (int t = 0; t < 9; ++t) acc[j][t] += __shfl_down_sync(0xffffffffu, acc[j][t], 12);
     }
-    // combine the 8 pixel partitions: 4..7 -> 0..3, 2..3 -> 0..1, 1 -> 0 (fixed order: deterministic)
+    // combine the 8 warps: 4..7 -> 0..3, 2..3 -> 0..1, 1 -> 0 (fixed order: deterministic)
 #pragma unroll
     for (int half = 4; half >= 1; half >>= 1) {
       __syncthreads();               // previous readers of `red` (or of the patch it aliases) are done
-      if (pp >= half && pp < 2 * half) {
-        float* dst = red + ((size_t)(pp - half) * 32 + lane) * 54;
+      if (warp >= half && warp < 2 * half) {
+        float* dst = red + ((size_t)(warp - half) * 32 + lane) * 54;
 #pragma unroll
         for (int j = 0; j < 6; ++j)
 #pragma unroll
           for (int t = 0; t < 9; ++t) dst[j * 9 + t] = acc[j][t];
       }
       __syncthreads();
-      if (pp < half) {
-        const float* src = red + ((size_t)pp * 32 + lane) * 54;
+      if (warp < half) {
+        const float* src = red + ((size_t)warp * 32 + lane) * 54;
 #pragma unroll
         for (int j = 0; j < 6; ++j)
 #pragma unroll
           for (int t = 0; t < 9; ++t) acc[j][t] += src[j * 9 + t];
       }
     }
-    if (pp == 0) {
+    if (warp == 0 && (CIN == 3 ? lane < 12 : true)) {
 #pragma unroll
       for (int j = 0; j < 6; ++j)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) out[((size_t)(cg * 6 + j) * kC + ci0 + ci) * 9 + t] = acc[j][t];
+        for (int t = 0; t < 9; ++t) out[((size_t)(cg * 6 + j) * CIN + ci0 + ci) * 9 + t] = acc[j][t];
     }
   }
 }
@@ -570,7 +556,7 @@ __global__ void __launch_bounds__(256)
 conv_dgrad_kernel(const float* __restrict__ yout, const float* __restrict__ dAout, const float* __restrict__ aff_out,
                   const float* __restrict__ coef, const float* __restrict__ w, float* __restrict__ dA, int hin, int hout,
                   int tiles_x) {
-  __shared__ float dys[kC][kTile + 1][kTile + 2];
+  __shared__ __align__(16) float dys[kC][kTile + 1][kTile + 4];
   __shared__ __align__(16) float wsm[kC][kChunk][12];
   const int tid = threadIdx.x, tx = tid % kTile, ty = tid / kTile;
   const int b = blockIdx.y, ci0 = blockIdx.z * kChunk;
@@ -578,14 +564,7 @@ conv_dgrad_kernel(const float* __restrict__ yout, const float* __restrict__ dAou
   const float* yb_o = yout + (size_t)b * kC * hout * hout;
   const float* dab = dAout + (size_t)b * kC * hout * hout;
 
-#pragma unroll 8
-  for (int idx = tid; idx < kC * (kTile + 1) * (kTile + 1); idx += 256) {
-    const int co = idx / ((kTile + 1) * (kTile + 1)), rem = idx % ((kTile + 1) * (kTile + 1));
-    const int r = rem / (kTile + 1), c = rem % (kTile + 1);
-    const int oh = q0y + r, ow = q0x + c;
-    const size_t o_ = ((size_t)co * hout + oh) * hout + ow;
-    dys[co][r][c] = (oh < hout && ow < hout) ? bn_bwd_dy(yb_o[o_], dab[o_], aff_out, coef, co) : 0.f;
-  }
+  stage_dy<kTile + 1, kTile + 1, kTile + 4, (kTile + 1) * (kTile + 4)>(&dys[0][0][0], yb_o, dab, aff_out, coef, q0y, q0x, hout, tid);
   for (int idx = tid; idx < kC * kChunk * 9; idx += 256) {
     const int co = idx / (kChunk * 9), rem = idx % (kChunk * 9);
     const int ci = rem / 9, t = rem % 9;
@@ -628,10 +607,6 @@ conv_dgrad_kernel(const float* __restrict__ yout, const float* __restrict__ dAou
       *reinterpret_cast<float2*>(&oc[(size_t)(ih + 1) * hin + iw]) = make_float2(acc[ci][2], acc[ci][3]);
     }
   }
-}
-
-static size_t wgrad_smem_bytes(int cc) {
-  return ((size_t)cc * kPatch * kPW + (size_t)kC * kTile * kTile + (size_t)5 * 6 * cc * 37) * sizeof(float);
 }
 
 constexpr int kRedChunks = 64;      // row chunks of the two-stage fixed-order reduction of the wgrad partials
@@ -769,13 +744,13 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float
     dim3 grid(p.tiles[l], cfg->B);
     const int cin = l == 0 ? 3 : kC;
     if (l == 0) {
-      const size_t smem = wgrad_smem_bytes(3);
+      const size_t smem = wgrad_smem_bytes<3>();
       RN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       conv_wgrad_kernel<3><<<grid, 256, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, hin, hout, tx);
     } else {
-      const size_t smem = wgrad24_smem_bytes();
-      RN_CUDA(cudaFuncSetAttribute(conv_wgrad24_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conv_wgrad24_kernel<<<grid, 256, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, hin, hout, tx);
+      const size_t smem = wgrad_smem_bytes<kC>();
+      RN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv_wgrad_kernel<kC><<<grid, 256, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, hin, hout, tx);
     }
     RN_LAUNCH_CHECK("conv_wgrad_kernel");
     {
