@@ -247,6 +247,11 @@ def run_ours(args):
                 dst.copy_(src, non_blocking=True)
             ready[slot].record(copy_stream)
 
+    # the loss of every step is copied to pinned host memory on the compute stream and read one step later, so the
+    # host never stalls the launch queue (the reference reads loss.data[0] every step, train.py:51)
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_loop(n):
         losses = []
         stage(0)
@@ -257,7 +262,13 @@ def run_ours(args):
             torch.cuda.current_stream().wait_event(ready[slot])
             l = train_step(model, opt, *bufs[slot])
             consumed[slot].record()
-            losses.append(float(l.detach()))  # device -> host read of the step's result, every step
+            loss_host[slot].copy_(l.detach(), non_blocking=True)      # device -> host read of the step's result, every step
+            loss_ready[slot].record()
+            if i > 0:
+                loss_ready[1 - slot].synchronize()
+                losses.append(float(loss_host[1 - slot]))
+        loss_ready[(n - 1) % 2].synchronize()
+        losses.append(float(loss_host[(n - 1) % 2]))
         return losses
 
     for ev in consumed:

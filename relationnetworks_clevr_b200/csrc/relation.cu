@@ -139,10 +139,151 @@ int relation_qinj_bwd(const RelShape& s, int l, const float* q, const float* con
   return RN_OK;
 }
 
+// Fused layer-0 backward for the from-pixels shapes (k == 26, n == 64, G == 256).  Persistent blocks of 256 threads walk
+// the samples; dU[b] / dV[b] ([64, 256] each) are staged in shared memory with a 257-float row stride so that both
+// access patterns below are conflict-free:
+//   phase A (thread = feature g): delta0[b, g] = sum_a dV[a, g];  dW0c[g, :] += dU[c, g] x[c, :];  dW0a[g, :] += dV[a, g] x[a, :]
+//                                 (52 register accumulators per thread, carried over all samples of the block)
+//   phase B (thread = object o x K-quarter): dX[b, o, :] = dU[o, :] W0c + dV[o, :] W0a  (K = 256 features, 4-way split)
+// Per-block partials of dW0 / db0 are summed in a fixed order by layer0_bwd_reduce_kernel.  The question-injection
+// terms use delta0 (written to global) through the small GEMMs of relation_qinj_bwd.
+constexpr int kL0N = 64, kL0K = 26, kL0G = 256, kL0Ld = kL0G + 1;
+static size_t layer0_bwd_smem() {
+  return ((size_t)2 * kL0N * kL0Ld + (size_t)kL0G * 2 * kL0K + (size_t)kL0N * kL0K + (size_t)4 * kL0N * 28) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(256)
+layer0_bwd_fused_kernel(const float* __restrict__ dU, const float* __restrict__ dV, const float* __restrict__ x,
+                        const float* __restrict__ w0, int fan0, int B, float* __restrict__ delta, float* __restrict__ dx,
+                        float* __restrict__ part) {
+  extern __shared__ __align__(16) float l0_smem[];
+  float* us = l0_smem;                              // [64][257]
+  float* vs = us + kL0N * kL0Ld;                    // [64][257]
+  float* ws = vs + kL0N * kL0Ld;                    // [256][52]: W0c | W0a rows
+  float* xs = ws + kL0G * 2 * kL0K;                 // [64][26]
+  float* red = xs + kL0N * kL0K;                    // [4][64][28]
+  const int tid = threadIdx.x, g = tid;
+  for (int base = 0; base < kL0G * 2 * kL0K; base += 8 * 256) {
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * 256 + tid;
+      t[u] = idx < kL0G * 2 * kL0K ? w0[(size_t)(idx / (2 * kL0K)) * fan0 + idx % (2 * kL0K)] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * 256 + tid;
+      if (idx < kL0G * 2 * kL0K) ws[idx] = t[u];
+    }
+  }
+  float wc[kL0K], wa[kL0K], db = 0.f;
+#pragma unroll
+  for (int j = 0; j < kL0K; ++j) wc[j] = wa[j] = 0.f;
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();            // previous sample fully consumed (also orders the ws fill)
+    const float* du = dU + (size_t)b * kL0N * kL0G;
+    const float* dv = dV + (size_t)b * kL0N * kL0G;
+#pragma unroll 1
+    for (int o0 = 0; o0 < kL0N; o0 += 8) {          // 16 coalesced row loads in flight per thread
+      float tu[8], tv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        tu[i] = du[(size_t)(o0 + i) * kL0G + g];
+        tv[i] = dv[(size_t)(o0 + i) * kL0G + g];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        us[(o0 + i) * kL0Ld + g] = tu[i];
+        vs[(o0 + i) * kL0Ld + g] = tv[i];
+      }
+    }
+    for (int i = tid; i < kL0N * kL0K; i += 256) xs[i] = x[(size_t)b * kL0N * kL0K + i];
+    __syncthreads();
+
+    // ---- phase A ----
+    float d0 = 0.f;
+#pragma unroll 2
+    for (int o = 0; o < kL0N; ++o) {
+      const float u = us[o * kL0Ld + g], v = vs[o * kL0Ld + g];
+      d0 += v;
+#pragma unroll
+      for (int j = 0; j < kL0K; j += 2) {
+        const float2 xv = *reinterpret_cast<const float2*>(&xs[o * kL0K + j]);
+        wc[j] = fmaf(u, xv.x, wc[j]);
+        wc[j + 1] = fmaf(u, xv.y, wc[j + 1]);
+        wa[j] = fmaf(v, xv.x, wa[j]);
+        wa[j + 1] = fmaf(v, xv.y, wa[j + 1]);
+      }
+    }
+    delta[(size_t)b * kL0G + g] = d0;
+    db += d0;
+
+    // ---- phase B ----
+    {
+      const int o = tid & 63, kq = tid >> 6;
+      float acc[kL0K];
+#pragma unroll
+      for (int j = 0; j < kL0K; ++j) acc[j] = 0.f;
+#pragma unroll 2
+      for (int gg = kq * 64; gg < kq * 64 + 64; ++gg) {
+        const float u = us[o * kL0Ld + gg], v = vs[o * kL0Ld + gg];
+        const float* wr = ws + gg * 2 * kL0K;         // warp-uniform: broadcast reads
+#pragma unroll
+        for (int j = 0; j < kL0K; j += 2) {
+          const float2 c2 = *reinterpret_cast<const float2*>(wr + j);
+          const float2 a2 = *reinterpret_cast<const float2*>(wr + kL0K + j);
+          acc[j] = fmaf(u, c2.x, fmaf(v, a2.x, acc[j]));
+          acc[j + 1] = fmaf(u, c2.y, fmaf(v, a2.y, acc[j + 1]));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kL0K; ++j) red[(kq * kL0N + o) * 28 + j] = acc[j];
+    }
+    __syncthreads();
+    for (int i = tid; i < kL0N * kL0K; i += 256) {
+      const int o = i / kL0K, j = i % kL0K;
+      dx[(size_t)b * kL0N * kL0K + i] = (red[(0 * kL0N + o) * 28 + j] + red[(1 * kL0N + o) * 28 + j]) +
+                                        (red[(2 * kL0N + o) * 28 + j] + red[(3 * kL0N + o) * 28 + j]);
+    }
+  }
+  float* pr = part + (size_t)blockIdx.x * (kL0G * (2 * kL0K + 1));
+#pragma unroll
+  for (int j = 0; j < kL0K; ++j) {
+    pr[g * (2 * kL0K + 1) + j] = wc[j];
+    pr[g * (2 * kL0K + 1) + kL0K + j] = wa[j];
+  }
+  pr[g * (2 * kL0K + 1) + 2 * kL0K] = db;
+}
+
+// dW0[g, 0:52] and db0[g] = fixed-order sums of the per-block partials
+__global__ void layer0_bwd_reduce_kernel(const float* __restrict__ part, int nblk, float* __restrict__ dw0, int fan0,
+                                         float* __restrict__ db0) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int W = 2 * kL0K + 1;
+  if (idx >= kL0G * W) return;
+  float v = 0.f;
+  for (int i = 0; i < nblk; ++i) v += part[(size_t)i * kL0G * W + idx];
+  const int g = idx / W, j = idx % W;
+  if (j < 2 * kL0K) dw0[(size_t)g * fan0 + j] = v;
+  else db0[g] = v;
+}
+
 int relation_layer0_bwd(const RelShape& s, const float* x, const float* q, const float* const* g_w, const float* dU,
                         const float* dV, float* delta, float* dx, float* dq, float* const* dg_w,
                         float* const* dg_b, float* ws, size_t ws_floats, cudaStream_t st) {
   const int fan0 = s.fan_in(0);
+  const int nblk = std::min(s.B, sm_count());
+  if (s.k == kL0K && s.n == kL0N && s.G == kL0G && ws && ws_floats >= (size_t)nblk * kL0G * (2 * kL0K + 1)) {
+    const size_t smem = layer0_bwd_smem();
+    RN_CUDA(cudaFuncSetAttribute(layer0_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    layer0_bwd_fused_kernel<<<nblk, 256, smem, st>>>(dU, dV, x, g_w[0], fan0, s.B, delta, dx, ws);
+    RN_LAUNCH_CHECK("layer0_bwd_fused_kernel");
+    layer0_bwd_reduce_kernel<<<cdiv(kL0G * (2 * kL0K + 1), 256), 256, 0, st>>>(ws, nblk, dg_w[0], fan0, dg_b[0]);
+    RN_LAUNCH_CHECK("layer0_bwd_reduce_kernel");
+    if (s.qinj == 0) RN_TRY(relation_qinj_bwd(s, 0, q, g_w, delta, dq, dg_w, st));
+    return RN_OK;
+  }
   GemmEpilogue none, acc;
   acc.beta = 1.f;
   // delta0[b] = sum_a dV[b,a]   (== sum over all pairs of dZ1) ; db0 = sum_b delta0

@@ -221,17 +221,18 @@ __device__ __forceinline__ void generate_h1_n64(const ChainParams& p, int tile, 
     for (int h = 0; h < 2; ++h) v[ai][h] = __ldg(reinterpret_cast<const float4*>(Vb + ai * kG + h * 128));
   char* dst0 = a_tile + (lane >> 4) * kAChunk + ((4 * lane) & 7) * 2;       // + row part + swizzled group
   const int grp = ((4 * lane) & 63) >> 3;
+  constexpr int RB = SAVE ? 4 : 8;              // rows per batch: 2*RB loads in flight (the ballot path is register-tight)
 #pragma unroll 1
-  for (int it = 0; it < 16; it += 4) {
-    float4 u[4][2];
+  for (int it = 0; it < 16; it += RB) {
+    float4 u[RB][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < RB; ++i) {
       const int c = q * 16 + it + i;
 #pragma unroll
       for (int h = 0; h < 2; ++h) u[i][h] = __ldg(reinterpret_cast<const float4*>(Ub + (size_t)c * kG + h * 128));
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < RB; ++i) {
       const int c = q * 16 + it + i;
       uint32_t mine = 0;
 #pragma unroll
@@ -263,38 +264,34 @@ __device__ __forceinline__ void generate_h1_n64(const ChainParams& p, int tile, 
 }
 
 // Backward generation: dZ4[r, :] = S * dxg[b, :] where Z4[r, :] > 0 -> swizzled fp16 A operand.
-// Same lane mapping as generate_h1.  (Column sums of the dZ images are taken by the weight-gradient kernel.)
+// Warp q owns rows [32q, 32q+32); lane owns columns [8*lane, 8*lane+8) of every row: the packed fp16 pairs of
+// S * dxg for those columns are built once per tile, and a row costs one mask-word load (all 32 issued up front: one
+// exposed L2 round trip per tile), four pair-mask ANDs and one conflict-free STS.128.
+// (Column sums of the dZ images are taken by the weight-gradient kernel.)
 __device__ __forceinline__ void generate_dz4(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
   const int b = tile / p.tiles_per_sample;
-  const int sub = lane >> 3, j = lane & 7;
   const float S = __ldg(p.scale);
-  float d[kNKC][8];
+  const float4 d0 = __ldg(reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + lane * 8));
+  const float4 d1 = __ldg(reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + lane * 8 + 4));
+  const uint32_t dp[4] = {pack_half2(d0.x * S, d0.y * S), pack_half2(d0.z * S, d0.w * S), pack_half2(d1.x * S, d1.y * S),
+                          pack_half2(d1.z * S, d1.w * S)};
+  // cols 8*lane + e of a row live in word lane / 4 at bit (lane % 4) * 4 + e / 2 + 16 * (e % 2)
+  const uint32_t* m4 = p.masks + (((size_t)3 * p.num_tiles + tile) * kTileM + q * 32) * 8 + (lane >> 2);
+  const int sh = (lane & 3) * 4;
+  uint32_t w[32];
 #pragma unroll
-  for (int kc = 0; kc < kNKC; ++kc) {
-    const float4 d0 = __ldg(reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + kc * 64 + j * 8));
-    const float4 d1 = __ldg(reinterpret_cast<const float4*>(p.dxg + (size_t)b * kG + kc * 64 + j * 8 + 4));
-    d[kc][0] = d0.x * S; d[kc][1] = d0.y * S; d[kc][2] = d0.z * S; d[kc][3] = d0.w * S;
-    d[kc][4] = d1.x * S; d[kc][5] = d1.y * S; d[kc][6] = d1.z * S; d[kc][7] = d1.w * S;
-  }
-  const uint32_t* m4 = p.masks + ((size_t)3 * p.num_tiles + tile) * kTileM * 8;
-#pragma unroll 2
-  for (int g = 0; g < 8; ++g) {
-    const int row = q * 32 + g * 4 + sub;
-    // cols kc*64 + j*8 + e live in word kc*2 + (j >> 2) at bit (j & 3)*4 + e/2 + 16*(e%2)
+  for (int r = 0; r < 32; ++r) w[r] = __ldg(m4 + r * 8);
+  char* dst = a_tile + (lane >> 3) * kAChunk;
 #pragma unroll
-    for (int kc = 0; kc < kNKC; ++kc) {
-      const uint32_t word = __ldg(m4 + (size_t)row * 8 + kc * 2 + (j >> 2));
-      const uint32_t nib = word >> ((j & 3) * 4);       // bit e/2 (even e) and 16 + e/2 (odd e) of this lane's 8 columns
-      float h[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) h[e] = ((nib >> mask_pos(e)) & 1u) ? d[kc][e] : 0.f;
-      uint4 o;
-      o.x = pack_half2(h[0], h[1]);
-      o.y = pack_half2(h[2], h[3]);
-      o.z = pack_half2(h[4], h[5]);
-      o.w = pack_half2(h[6], h[7]);
-      *reinterpret_cast<uint4*>(a_tile + kc * kAChunk + sw128_offset(row, j * 8)) = o;
-    }
+  for (int r = 0; r < 32; ++r) {
+    const int row = q * 32 + r;
+    const uint32_t nib = w[r] >> sh;
+    uint4 o;
+    o.x = dp[0] & (((nib >> 0) & 0x00010001u) * 0xFFFFu);      // pair (e, e+1): bits e/2 and 16 + e/2 -> 0xFFFF per half
+    o.y = dp[1] & (((nib >> 1) & 0x00010001u) * 0xFFFFu);
+    o.z = dp[2] & (((nib >> 2) & 0x00010001u) * 0xFFFFu);
+    o.w = dp[3] & (((nib >> 3) & 0x00010001u) * 0xFFFFu);
+    *reinterpret_cast<uint4*>(dst + sw128_offset(row, (lane & 7) * 8)) = o;
   }
 }
 
@@ -586,7 +583,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
               float x[32];
               uint32_t bits = 0;
 #pragma unroll
-              for (int e = 0; e < 32; ++e) x[e] = fmaxf(__uint_as_float(r[e]) + __ldg(bias + cc * 32 + e), 0.f);
+              for (int e4 = 0; e4 < 8; ++e4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + e4 * 4));
+                x[e4 * 4 + 0] = fmaxf(__uint_as_float(r[e4 * 4 + 0]) + bv.x, 0.f);
+                x[e4 * 4 + 1] = fmaxf(__uint_as_float(r[e4 * 4 + 1]) + bv.y, 0.f);
+                x[e4 * 4 + 2] = fmaxf(__uint_as_float(r[e4 * 4 + 2]) + bv.z, 0.f);
+                x[e4 * 4 + 3] = fmaxf(__uint_as_float(r[e4 * 4 + 3]) + bv.w, 0.f);
+              }
               if (SAVE) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) bits |= half2_pos_mask(pack_half2(x[2 * i], x[2 * i + 1])) & mask_pair_const(i);
