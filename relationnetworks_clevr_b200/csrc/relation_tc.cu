@@ -33,6 +33,7 @@ constexpr int kWChunk = kG * kKC * 2;         // 32 KB
 constexpr int kStages = 3;
 constexpr int kTcLayers = 3;            // g layers 1..3 run on the tensor cores
 constexpr int kFwdThreads = 384;
+constexpr int kGenThreads = 512;          // + one generator warpgroup (warps 12..15)
 constexpr int kSmemA = 0;
 constexpr int kSmemW = 2 * kATile;
 constexpr int kSmemBar = kSmemW + kStages * kWChunk;
@@ -122,6 +123,8 @@ struct Bars {
   uint64_t peer_full[kStages2];   // CTA-pair mode, leader only: the peer CTA's half of the chunk has landed
   uint64_t a_full[2];
   uint64_t acc_full[2];
+  uint64_t a_free[2];             // generator mode: the slot's A buffer may be overwritten with the next tile's operand
+  uint64_t h1_done[2];            // generator mode: the image store of the generated operand has finished reading A
   uint32_t tmem_base;
 };
 
@@ -334,8 +337,12 @@ __device__ long long g_chain_prof[160][16];
 #define PROF_T0() long long _t0 = 0; if (prof) _t0 = clock64();
 #define PROF_ACC(i) if (prof) { const long long _t1 = clock64(); pacc[i] += _t1 - _t0; _t0 = _t1; }
 
-template <int MODE, bool CTA2>
-__global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainParams p) {
+// GEN = true (single-CTA form only): a fourth warpgroup generates the layer-1 operand of each slot's NEXT tile as
+// soon as the slot's last MMA has released the A buffer, concurrently with the slot's own last-layer epilogue (which
+// only reads TMEM), instead of the epilogue warps doing both back to back on the slot's critical path.
+template <int MODE, bool CTA2, bool GEN>
+__global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain_kernel(const ChainParams p) {
+  static_assert(!(GEN && CTA2), "generator warpgroup: single-CTA form only");
   constexpr bool SAVE = MODE != kFwdEval;        // training forward and dgrad stream operand images to HBM
   constexpr int NST = CTA2 ? kStages2 : kStages;
   constexpr int STAGE_BYTES = CTA2 ? kWHalf : kWChunk;
@@ -357,8 +364,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
       mbar_init(smem_u32(&bars->peer_full[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bars->a_full[s]), CTA2 ? 8 : 128);       // pair mode: one arrival per warp, from both CTAs, at the leader
+      // pair mode: one arrival per warp, from both CTAs, at the leader.  generator mode: 128 generator + 128 epilogue arrivals
+      mbar_init(smem_u32(&bars->a_full[s]), CTA2 ? 8 : GEN ? 256 : 128);
       mbar_init(smem_u32(&bars->acc_full[s]), 1);
+      mbar_init(smem_u32(&bars->a_free[s]), 1);
+      mbar_init(smem_u32(&bars->h1_done[s]), 1);
     }
     fence_mbar_init();
   }
@@ -371,8 +381,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
   else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
-
   // job sequence shared by producer and issuer: for round r: for layer 0..2: for slot 0..1 (if its tile exists)
+  // generator mode re-balances registers per warpgroup: 56*128 + 176*256 + 96*128 = 64512
+  if (warp < 4) {
+  if (GEN) reg_dec<56>();
   if (warp == 0) {
     if (lane == 0) {
       // ================= weight producer =================
@@ -457,8 +469,50 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else if (GEN && warp >= 12) {
+    // ================= generator warpgroup =================
+    reg_dec<96>();
+    const int q = warp & 3, gtid = threadIdx.x - 384;
+    uint32_t free_phase[2] = {0, 0};
+    const bool prof = (p.dbg & 8) != 0 && gtid == 0;
+    long long pacc[2] = {0, 0};
+    PROF_T0();
+    for (int i = 0; i < my_tiles; ++i) {
+      const int s = i & 1;
+      const int tile = tile_first + i * tile_step;
+      char* a_tile = smem + kSmemA + s * kATile;
+      mbar_wait(smem_u32(&bars->a_free[s]), free_phase[s] ^ 1);       // passes at once for the slot's first tile
+      free_phase[s] ^= 1;
+      PROF_ACC(0);
+      if (MODE == kDgrad) generate_dz4(p, tile, a_tile, q, lane);
+      else if (p.n == 64) generate_h1_n64<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
+      else generate_h1<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
+      fence_proxy_async_smem();
+      if (SAVE) {
+        named_bar_sync(3, 128);                   // whole image written and fenced by every generator thread
+        if (gtid == 0) {
+          char* dst = MODE == kFwdTrain ? reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile
+                                        : reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + 3) * kATile;
+          bulk_s2g(dst, smem_u32(a_tile), kATile);
+          bulk_commit();
+        }
+      }
+      mbar_arrive(smem_u32(&bars->a_full[s]));
+      PROF_ACC(1);
+      if (SAVE && gtid == 0) {
+        bulk_wait_read0();
+        mbar_arrive(smem_u32(&bars->h1_done[s]));
+      }
+    }
+    if (SAVE && gtid == 0) bulk_wait0();
+    if (prof) {
+      g_chain_prof[blockIdx.x][6] = pacc[0];
+      g_chain_prof[blockIdx.x][7] = pacc[1];
+    }
+  } else {
     // ================= generation / epilogue warpgroups =================
+    if (GEN) reg_inc<176>();
     const int s = (warp - 4) >> 2;             // tile slot
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
@@ -479,10 +533,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
       if (CTA2) {
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(a_full);
+      } else if (GEN) {
+        mbar_arrive_n(a_full, 2);              // the barrier expects 256 arrivals (generator mode)
       } else {
         mbar_arrive(a_full);
       }
     };
+    uint32_t h1_phase = 0;
     // stream the freshly written operand image of this slot to HBM (one elected thread, bulk async store)
     auto store_image = [&](char* dst) {
       named_bar_sync(bar_id, 128);              // whole image written and fenced by every thread
@@ -505,14 +562,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
       const int tile = tile_first + i * tile_step;
       const int b = tile / p.tiles_per_sample;
       if (prof) _t0 = clock64();
-      if (SAVE) wait_image_read();
-      if (MODE == kDgrad) generate_dz4(p, tile, a_tile, q, lane);
-      else if (p.n == 64) generate_h1_n64<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
-      else generate_h1<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
-      fence_proxy_async_smem();
-      if (MODE == kFwdTrain) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile);
-      if (MODE == kDgrad) store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + 3) * kATile);
-      arrive_a_full();
+      if (GEN) {
+        // this slot's accumulator has been drained (or never used): the epilogue half of "operand + accumulator ready"
+        tc_fence_before_sync();
+        mbar_arrive(a_full);
+      } else {
+        if (SAVE) wait_image_read();
+        if (MODE == kDgrad) generate_dz4(p, tile, a_tile, q, lane);
+        else if (p.n == 64) generate_h1_n64<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
+        else generate_h1<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
+        fence_proxy_async_smem();
+        if (MODE == kFwdTrain) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile);
+        if (MODE == kDgrad) store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + 3) * kATile);
+        arrive_a_full();
+      }
       PROF_ACC(0);
 
       for (int layer = 0; layer < kTcLayers; ++layer) {
@@ -526,7 +589,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
           PROF_ACC(1);
           tc_fence_after_sync();
           if (layer < kTcLayers - 1) {
-            if (SAVE) wait_image_read();
+            if (GEN && SAVE && layer == 0) {       // the generator's image store of H1 must have finished reading A
+              mbar_wait(smem_u32(&bars->h1_done[s]), h1_phase);
+              h1_phase ^= 1;
+            } else if (SAVE) {
+              wait_image_read();
+            }
             uint32_t mw[8];
             if (p.dbg & 2) {
 #pragma unroll
@@ -573,6 +641,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
             PROF_ACC(2);
           } else {
             // last layer: ReLU + pair-sum.  Column sums over this warp's 32 rows by shuffle transpose-reduce.
+            if (GEN && wg_tid == 0) {              // the last MMA has read A (and so has the H3 image store): hand it to the generator
+              if (SAVE) bulk_wait_read0();
+              mbar_arrive(smem_u32(&bars->a_free[s]));
+            }
             float* part = p.xg_part + ((size_t)tile * 4 + q) * kG;
             uint32_t mw[8];
 #pragma unroll
@@ -615,18 +687,36 @@ __global__ void __launch_bounds__(kFwdThreads, 1) rn_g_chain_kernel(const ChainP
           acc_phase ^= 1;
           PROF_ACC(1);
           tc_fence_after_sync();
-          wait_image_read();
-          if (!(p.dbg & 2)) {
-            // Z2..Z4 masks: word cc, bit mask_pos(e).  Z1 mask: lane-local layout of generate_h1 (column c -> word
-            // (c % 64) / 8, bit (c / 64) * 4 + (c % 8) / 2 + 16 * (c % 2)) or the ballot layout of generate_h1_n64.
-            if (l != 1) dgrad_mask_tile<0>(taddr, mw, a_tile, swz);
-            else if (p.n == 64) dgrad_mask_tile<2>(taddr, mw, a_tile, swz);
-            else dgrad_mask_tile<1>(taddr, mw, a_tile, swz);
+          char* img = reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + (l - 1)) * kATile;
+          if (GEN && l == 1) {
+            // generator mode: dZ1 goes straight from registers to its HBM image (same swizzled offsets), so the A buffer is
+            // free for the next tile's dZ4 as soon as the dZ2 image store has finished reading it
+            if (wg_tid == 0) {
+              bulk_wait_read0();
+              mbar_arrive(smem_u32(&bars->a_free[s]));
+            }
+            if (p.n == 64) dgrad_mask_tile<2>(taddr, mw, img, swz);
+            else dgrad_mask_tile<1>(taddr, mw, img, swz);
+            tc_fence_before_sync();
+          } else {
+            if (GEN && layer == 0) {                 // the generator's dZ4 image store must have finished reading A
+              mbar_wait(smem_u32(&bars->h1_done[s]), h1_phase);
+              h1_phase ^= 1;
+            } else {
+              wait_image_read();
+            }
+            if (!(p.dbg & 2)) {
+              // Z2..Z4 masks: word cc, bit mask_pos(e).  Z1 mask: lane-local layout of generate_h1 (column c -> word
+              // (c % 64) / 8, bit (c / 64) * 4 + (c % 8) / 2 + 16 * (c % 2)) or the ballot layout of generate_h1_n64.
+              if (l != 1) dgrad_mask_tile<0>(taddr, mw, a_tile, swz);
+              else if (p.n == 64) dgrad_mask_tile<2>(taddr, mw, a_tile, swz);
+              else dgrad_mask_tile<1>(taddr, mw, a_tile, swz);
+            }
+            fence_proxy_async_smem();
+            store_image(img);
+            tc_fence_before_sync();
+            if (layer < kTcLayers - 1) arrive_a_full();
           }
-          fence_proxy_async_smem();
-          store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + (l - 1)) * kATile);
-          tc_fence_before_sync();
-          if (layer < kTcLayers - 1) arrive_a_full();
           PROF_ACC(2);
         }
       }
@@ -1046,7 +1136,7 @@ static int launch_chain(const ChainParams& p, cudaStream_t st) {
   static const bool allow_pair = []() { const char* e = getenv("RN_B200_CTA2"); return e && e[0] == '1'; }();
   if (allow_pair && p.num_tiles % 2 == 0 && p.num_tiles >= 2) {
     const int pairs = std::min(p.num_tiles / 2, sm_count() / 2);
-    RN_CUDA(cudaFuncSetAttribute(rn_g_chain_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    RN_CUDA(cudaFuncSetAttribute(rn_g_chain_kernel<MODE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(kFwdThreads);
@@ -1059,13 +1149,24 @@ static int launch_chain(const ChainParams& p, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RN_CUDA(cudaLaunchKernelEx(&cfg, rn_g_chain_kernel<MODE, true>, p));
+    RN_CUDA(cudaLaunchKernelEx(&cfg, rn_g_chain_kernel<MODE, true, false>, p));
     RN_LAUNCH_CHECK("rn_g_chain_kernel<pair>");
     return RN_OK;
   }
   const int grid = std::min(p.num_tiles, sm_count());
-  RN_CUDA(cudaFuncSetAttribute(rn_g_chain_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
-  rn_g_chain_kernel<MODE, false><<<grid, kFwdThreads, kSmemLaunch, st>>>(p);
+  // Generator-warpgroup form: measured at B=640 it hides the tile boundary in the eval forward (1.65 vs 1.68 ms) but not
+  // in the training forward / data gradient, where the extra warpgroup competes with the epilogue warps for issue slots
+  // and (dgrad) dZ1 has to be stored straight from registers (2.28 vs 2.22 ms, 3.38 vs 3.19 ms).  Default: eval only;
+  // RN_B200_GENWG=0 / 1 forces the 384-thread / 512-thread form everywhere.
+  static const int gen_env = []() { const char* e = getenv("RN_B200_GENWG"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+  const bool gen_wg = gen_env < 0 ? MODE == kFwdEval : gen_env == 1;
+  if (gen_wg) {
+    RN_CUDA(cudaFuncSetAttribute(rn_g_chain_kernel<MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    rn_g_chain_kernel<MODE, false, true><<<grid, kGenThreads, kSmemLaunch, st>>>(p);
+  } else {
+    RN_CUDA(cudaFuncSetAttribute(rn_g_chain_kernel<MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    rn_g_chain_kernel<MODE, false, false><<<grid, kFwdThreads, kSmemLaunch, st>>>(p);
+  }
   RN_LAUNCH_CHECK("rn_g_chain_kernel");
   return RN_OK;
 }

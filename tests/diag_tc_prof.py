@@ -23,6 +23,7 @@ def read(tag):
     print(f"[{tag}] per slot-0 tile, mean over CTAs (cycles):")
     for i, nm in enumerate(names):
         print(f"    {nm:18s} {float((t[:, i] / tiles).mean()):10.0f}")
+    print(f"    generator per tile (both slots): wait_free {float((t[:, 6] / t[:, 5].clamp(min=1)).mean()):.0f}  gen {float((t[:, 7] / t[:, 5].clamp(min=1)).mean()):.0f}")
     rounds = tiles
     print(f"    issuer per round: wait_a {float((t[:, 8] / rounds).mean()):.0f}  wait_w {float((t[:, 9] / rounds).mean()):.0f}  "
           f"issue {float((t[:, 10] / rounds).mean()):.0f}")
