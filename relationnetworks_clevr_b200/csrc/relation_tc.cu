@@ -115,6 +115,7 @@ struct ChainParams {
   const float* scale;              // [0] = S (power of two applied to dxg), [1] = 1/S
   __half* dZ;                      // [tiles][4] x 64 KB images dZ1..dZ4 (scaled by S)
   int dbg;                         // timing ablations (RN_B200_DBG; results are garbage when nonzero)
+  int skip_dz4_image;              // dgrad: the weight-gradient kernel regenerates dZ4 from the sign bits
 };
 
 struct Bars {
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
         else generate_h1<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
         fence_proxy_async_smem();
         if (MODE == kFwdTrain) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile);
-        if (MODE == kDgrad) store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + 3) * kATile);
+        if (MODE == kDgrad && !p.skip_dz4_image) store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + 3) * kATile);
         arrive_a_full();
       }
       PROF_ACC(0);
@@ -750,7 +751,7 @@ constexpr int kWgThreads = 192;
 constexpr int kWgStageBytes = 65536;
 constexpr int kWgStages = 3;
 constexpr int kWgSmemBar = kWgStages * kWgStageBytes;
-constexpr int kWgSmemLaunch = kWgSmemBar + 128 + 1024;
+constexpr int kWgSmemLaunch = kWgSmemBar + 128 + 4096 + 1024;      // barriers, bit-count exchange (regen mode), alignment slack
 constexpr uint32_t kIdescWgrad = idesc_f16(kTileM, kG, 1, 1);
 
 struct WgradParams {
@@ -761,6 +762,13 @@ struct WgradParams {
   float* partial;          // [grid][256][256]
   float* colpart;          // [tiles][256]: column sums of each dZ tile (bias / question-injection gradients)
   int num_tiles;
+  // regen != 0 (layer 3): the dZ operand is dZ4 = S * dxg .* (Z4 > 0), regenerated here from the sign bits (32 B per
+  // row instead of a 512 B image row that the dgrad kernel would have to write and this kernel read back)
+  int regen;
+  const uint32_t* masks4;  // [tiles][128][8]
+  const float* dxg;        // [B, 256]
+  const float* scale;
+  int tiles_per_sample;
 };
 
 struct WgBars {
@@ -779,8 +787,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradPa
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kWgStages; ++s) {
-      mbar_init(smem_u32(&bars->full[s]), 1);
-      mbar_init(smem_u32(&bars->empty[s]), 1 + 4);      // MMA commit + the 4 column-sum warps
+      mbar_init(smem_u32(&bars->full[s]), p.regen ? 1 + 4 : 1);   // producer (+ the 4 generating warps)
+      mbar_init(smem_u32(&bars->empty[s]), p.regen ? 1 : 1 + 4);      // MMA commit (+ the 4 column-sum warps)
     }
     mbar_init(smem_u32(&bars->done), 1);
     fence_mbar_init();
@@ -799,11 +807,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradPa
         for (int half = 0; half < 2; ++half) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars->full[stage]);
-          mbar_expect_tx(full, kWgStageBytes);
+          mbar_expect_tx(full, p.regen ? kWgStageBytes / 2 : kWgStageBytes);
           const uint32_t dst = smem_u32(smem + stage * kWgStageBytes);
 #pragma unroll
           for (int c = 0; c < kNKC; ++c) {      // rows [64*half, 64*half+64) of column chunk c: 8 KB contiguous
-            bulk_g2s(dst + c * 8192, p.dZ + tile * p.dz_stride + c * kAChunk + half * 8192, 8192, full);
+            if (!p.regen) bulk_g2s(dst + c * 8192, p.dZ + tile * p.dz_stride + c * kAChunk + half * 8192, 8192, full);
             bulk_g2s(dst + 32768 + c * 8192, p.H + tile * p.h_stride + c * kAChunk + half * 8192, 8192, full);
           }
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
@@ -843,6 +851,76 @@ __global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradPa
       const uint32_t grp = (uint32_t)((col & 63) >> 3);
       uint32_t stage = 0, phase = 0;
       float2 acc = make_float2(0.f, 0.f);
+      if (p.regen) {
+        // Regenerate every dZ4 half tile into the stage's A slot: warp gw takes rows [16*gw, 16*gw + 16), lane owns columns
+        // [8*lane, 8*lane + 8) (chunk lane / 8, group lane % 8).  Mask words and dxg of the NEXT half tile are loaded while
+        // this one is generated.  Column sums (bias gradient) come from per-column bit counts: count * S*dxg.
+        const int gw = warp - 2;
+        const float S = __ldg(p.scale);
+        uint32_t* cnts = reinterpret_cast<uint32_t*>(smem + kWgSmemBar + 128);       // [2][4][128] packed 16-bit count pairs
+        const int sh = (lane & 3) * 4;
+        auto tile_of = [&](int i) { return (size_t)blockIdx.x + (size_t)(i >> 1) * gridDim.x; };
+        auto load_masks = [&](int i, uint32_t (&w)[16]) {
+          const uint32_t* m4 = p.masks4 + (tile_of(i) * kTileM + (i & 1) * 64 + gw * 16) * 8 + (lane >> 2);
+#pragma unroll
+          for (int r = 0; r < 16; ++r) w[r] = __ldg(m4 + r * 8);
+        };
+        uint32_t w[16], wn[16];
+        float4 d0, d1;
+        float2 dmine;
+        auto load_dxg = [&](int i) {
+          const float* row = p.dxg + (size_t)(tile_of(i) / p.tiles_per_sample) * kG;
+          d0 = __ldg(reinterpret_cast<const float4*>(row + lane * 8));
+          d1 = __ldg(reinterpret_cast<const float4*>(row + lane * 8 + 4));
+          dmine = __ldg(reinterpret_cast<const float2*>(row + col));
+        };
+        if (my_tiles > 0) { load_masks(0, w); load_dxg(0); }
+        for (int i = 0; i < 2 * my_tiles; ++i) {
+          const uint32_t dp[4] = {pack_half2(d0.x * S, d0.y * S), pack_half2(d0.z * S, d0.w * S),
+                                  pack_half2(d1.x * S, d1.y * S), pack_half2(d1.z * S, d1.w * S)};
+          const float2 vmine = __half22float2(__floats2half2_rn(dmine.x * S, dmine.y * S));     // the fp16 values that are summed
+          if (i + 1 < 2 * my_tiles) {
+            load_masks(i + 1, wn);
+            if (i & 1) load_dxg(i + 1);          // next tile
+          }
+          mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);          // the MMAs are done with this stage
+          char* dst = smem + stage * kWgStageBytes + (lane >> 3) * 8192;
+          uint32_t cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const int rl = gw * 16 + r;
+            const uint32_t nib = w[r] >> sh;
+            uint32_t b4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              b4[k] = (nib >> k) & 0x00010001u;      // pair (2k, 2k+1) of this lane's 8 columns: bit 0 / bit 16
+              cnt[k] += b4[k];
+            }
+            uint4 o;
+            o.x = dp[0] & (b4[0] * 0xFFFFu);
+            o.y = dp[1] & (b4[1] * 0xFFFFu);
+            o.z = dp[2] & (b4[2] * 0xFFFFu);
+            o.w = dp[3] & (b4[3] * 0xFFFFu);
+            *reinterpret_cast<uint4*>(dst + sw128_offset(rl, (lane & 7) * 8)) = o;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->full[stage]));
+          uint32_t* cb = cnts + (i & 1) * 512;
+          *reinterpret_cast<uint4*>(cb + gw * 128 + lane * 4) = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+          named_bar_sync(1, 128);
+          const uint32_t c4 = cb[t] + cb[128 + t] + cb[256 + t] + cb[384 + t];       // word t = columns 2t (low), 2t+1 (high)
+          acc.x += (float)(c4 & 0xFFFFu) * vmine.x;
+          acc.y += (float)(c4 >> 16) * vmine.y;
+          if (i & 1) {                                   // second half of the tile
+            *reinterpret_cast<float2*>(p.colpart + tile_of(i) * kG + col) = acc;
+            acc = make_float2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int r = 0; r < 16; ++r) w[r] = wn[r];
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+      } else {
       for (int i = 0; i < 2 * my_tiles; ++i) {
         mbar_wait(smem_u32(&bars->full[stage]), phase);
         const char* st = smem + stage * kWgStageBytes + coff;
@@ -861,6 +939,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradPa
           acc = make_float2(0.f, 0.f);
         }
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
       }
     }
     // final epilogue: TMEM lane quarters 2, 3, 0, 1
@@ -1244,6 +1323,10 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
   p.dxg = dxg;
   p.scale = ws.scale;
   p.dZ = ws.dZ;
+  // dZ4 is regenerated inside the layer-3 weight-gradient kernel (RN_B200_REGEN_DZ4=0: stream its image like dZ1..dZ3)
+  static const bool regen_dz4 = []() { const char* e = getenv("RN_B200_REGEN_DZ4"); return !(e && e[0] == '0'); }();
+  static const int gen_env = []() { const char* e = getenv("RN_B200_GENWG"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+  p.skip_dz4_image = (regen_dz4 && gen_env != 1) ? 1 : 0;      // (the generator-warpgroup form always stores it)
   RN_TRY(launch_chain<kDgrad>(p, st));
 
   // weight gradients of g layers 1..3: dW_l = dZ_{l+1}^T H_l
@@ -1258,6 +1341,11 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
     wp.partial = ws.partial;
     wp.colpart = ws.colpart + (size_t)(l - 1) * tiles * kG;
     wp.num_tiles = tiles;
+    wp.regen = (l == kTcLayers && p.skip_dz4_image) ? 1 : 0;
+    wp.masks4 = sv.masks + (size_t)3 * tiles * kTileM * 8;
+    wp.dxg = dxg;
+    wp.scale = ws.scale;
+    wp.tiles_per_sample = tps;
     rn_g_wgrad_kernel<<<wgrid, kWgThreads, kWgSmemLaunch, st>>>(wp);
     RN_LAUNCH_CHECK("rn_g_wgrad_kernel");
     wgrad_reduce_kernel<<<cdiv(kG * kG, 256), 256, 0, st>>>(ws.partial, wgrid, dg_w[l], s.fan_in(l), ws.scale);
