@@ -49,28 +49,70 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region, through NVML in a background thread (one cheap
+    query every 50 ms).  An `nvidia-smi -lms` subprocess is only the fallback: its full-device queries take driver
+    locks that stall kernel launches for tens of milliseconds each."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASON_BITS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self._stop = threading.Event()
+        self.nvml = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[self.index]) if self.index < len(ids) else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "250"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((mhz, self.max_mhz, mask))
+            except Exception:
+                pass
+            self._stop.wait(0.05)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+            rows = list(self.rows)
+            sm = [r[0] for r in rows]
+            reasons = sorted({name for r in rows for bit, name in self.REASON_BITS if r[2] & bit})
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
@@ -86,7 +128,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def synthetic_batch(B: int, seed: int):
@@ -176,6 +218,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (no "NCCL version ..." banner)
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.lib().rn_device_check(local_rank), "rn_device_check")
 
@@ -316,10 +360,11 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None,
                          # DRAM bytes of one forward+backward launch pair at B=640 (parity mode), from the committed ncu
-                         # capture profiles/r01_chain_wgrad_ncu_full.txt: chain fwd 4.49 GB + dgrad 5.73 GB + 3 x wgrad
-                         # 2.72 GB.  Far above the ~6 MB algorithmic bytes by design: training streams fp16 tile images
-                         # (H1..H3, dZ1..dZ4) through HBM for the weight-gradient GEMMs.
-                         "traffic": 18.4e9 if (precision == "parity" and B == 640) else None,
+                         # capture profiles/r01b_chain_wgrad_ncu_full.txt: chain fwd 4.47 GB + dgrad 4.30 GB + wgrad
+                         # 2.72 + 2.72 + 1.45 GB (+ dZ1 reduce 1.34 GB).  Far above the ~6 MB algorithmic bytes by design:
+                         # training streams fp16 tile images (H1..H3, dZ1..dZ3) through HBM for the weight-gradient GEMMs
+                         # (DESIGN.md section 4).
+                         "traffic": 17.0e9 if (precision == "parity" and B == 640) else None,
                          "kernel": "g-MLP (rn_relation_fwd + rn_relation_bwd launches)",
                          "relation_fwd_ms": fwd_ms, "relation_bwd_ms": bwd_ms,
                          "algorithmic_flop_per_launch_pair": G_FLOP_TRAIN * B, "peak_source": peaks["source"] + " (sustained bf16)"},
