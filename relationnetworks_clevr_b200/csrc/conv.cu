@@ -550,7 +550,7 @@ conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff
 // ------------------------------------------------------------------------------------------
 // data gradient (layers 2..4): dA_prev[b, ci, ih, iw] = sum_{co,kh,kw} dy[b, co, oh, ow] W[co, ci, kh, kw]
 // with ih = 2*oh + kh - 1.  Block: 32x32 input pixels of one image, thread = 2x2 input quad x 8 ci.
-// grid (tiles, B, 3 ci-chunks), block 256
+// grid (tiles, B), block 256; the three 8-channel chunks of ci are looped inside the block
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 conv_dgrad_kernel(const float* __restrict__ yout, const float* __restrict__ dAout, const float* __restrict__ aff_out,
@@ -559,52 +559,58 @@ conv_dgrad_kernel(const float* __restrict__ yout, const float* __restrict__ dAou
   __shared__ __align__(16) float dys[kC][kTile + 1][kTile + 4];
   __shared__ __align__(16) float wsm[kC][kChunk][12];
   const int tid = threadIdx.x, tx = tid % kTile, ty = tid / kTile;
-  const int b = blockIdx.y, ci0 = blockIdx.z * kChunk;
+  const int b = blockIdx.y;
   const int q0y = (blockIdx.x / tiles_x) * kTile, q0x = (blockIdx.x % tiles_x) * kTile;   // quad == output coords
   const float* yb_o = yout + (size_t)b * kC * hout * hout;
   const float* dab = dAout + (size_t)b * kC * hout * hout;
 
+  // dy of the window is staged ONCE and reused for the three 8-channel chunks of the input gradient
   stage_dy<kTile + 1, kTile + 1, kTile + 4, (kTile + 1) * (kTile + 4)>(&dys[0][0][0], yb_o, dab, aff_out, coef, q0y, q0x, hout, tid);
-  for (int idx = tid; idx < kC * kChunk * 9; idx += 256) {
-    const int co = idx / (kChunk * 9), rem = idx % (kChunk * 9);
-    const int ci = rem / 9, t = rem % 9;
-    wsm[co][ci][t] = w[((size_t)co * kC + ci0 + ci) * 9 + t];
-  }
-  __syncthreads();
-
-  // quad (i, j) covers input pixels (2i, 2j), (2i, 2j+1), (2i+1, 2j), (2i+1, 2j+1)
-  float acc[kChunk][4];
-#pragma unroll
-  for (int ci = 0; ci < kChunk; ++ci)
-#pragma unroll
-    for (int p = 0; p < 4; ++p) acc[ci][p] = 0.f;
-  if (2 * (q0y + (tid / 32) * 2) < hin)       // warp = quad rows 2w, 2w+1: skip warps entirely below the image
-#pragma unroll 1
-  for (int co = 0; co < kC; ++co) {
-    const float d00 = dys[co][ty][tx], d01 = dys[co][ty][tx + 1], d10 = dys[co][ty + 1][tx], d11 = dys[co][ty + 1][tx + 1];
-#pragma unroll
-    for (int ci = 0; ci < kChunk; ++ci) {
-      const float4 w0 = *reinterpret_cast<const float4*>(&wsm[co][ci][0]);   // taps (0,0) (0,1) (0,2) (1,0)
-      const float4 w1 = *reinterpret_cast<const float4*>(&wsm[co][ci][4]);   // taps (1,1) (1,2) (2,0) (2,1)
-      const float w22 = wsm[co][ci][8];
-      // (even, even): kh = 1, kw = 1
-      acc[ci][0] = fmaf(d00, w1.x, acc[ci][0]);
-      // (even, odd): kh = 1; kw = 0 -> ow = j + 1, kw = 2 -> ow = j
-      acc[ci][1] = fmaf(d01, w0.w, fmaf(d00, w1.y, acc[ci][1]));
-      // (odd, even): kw = 1; kh = 0 -> oh = i + 1, kh = 2 -> oh = i
-      acc[ci][2] = fmaf(d10, w0.y, fmaf(d00, w1.w, acc[ci][2]));
-      // (odd, odd): kh, kw in {0, 2}
-      acc[ci][3] = fmaf(d11, w0.x, fmaf(d10, w0.z, fmaf(d01, w1.z, fmaf(d00, w22, acc[ci][3]))));
-    }
-  }
+  const bool warp_active = 2 * (q0y + (tid / 32) * 2) < hin;      // warp = quad rows 2w, 2w+1: skip warps entirely below the image
   const int ih = 2 * (q0y + ty), iw = 2 * (q0x + tx);
-  if (ih < hin && iw < hin) {
-    float* o = dA + ((size_t)b * kC + ci0) * hin * hin;
+
+  for (int ci0 = 0; ci0 < kC; ci0 += kChunk) {
+    __syncthreads();                   // dys staged / previous chunk's weights no longer read
+    for (int idx = tid; idx < kC * kChunk * 9; idx += 256) {
+      const int co = idx / (kChunk * 9), rem = idx % (kChunk * 9);
+      const int ci = rem / 9, t = rem % 9;
+      wsm[co][ci][t] = w[((size_t)co * kC + ci0 + ci) * 9 + t];
+    }
+    __syncthreads();
+    if (!warp_active) continue;
+
+    // quad (i, j) covers input pixels (2i, 2j), (2i, 2j+1), (2i+1, 2j), (2i+1, 2j+1)
+    float acc[kChunk][4];
 #pragma unroll
-    for (int ci = 0; ci < kChunk; ++ci) {
-      float* oc = o + (size_t)ci * hin * hin;
-      *reinterpret_cast<float2*>(&oc[(size_t)ih * hin + iw]) = make_float2(acc[ci][0], acc[ci][1]);
-      *reinterpret_cast<float2*>(&oc[(size_t)(ih + 1) * hin + iw]) = make_float2(acc[ci][2], acc[ci][3]);
+    for (int ci = 0; ci < kChunk; ++ci)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[ci][p] = 0.f;
+#pragma unroll 1
+    for (int co = 0; co < kC; ++co) {
+      const float d00 = dys[co][ty][tx], d01 = dys[co][ty][tx + 1], d10 = dys[co][ty + 1][tx], d11 = dys[co][ty + 1][tx + 1];
+#pragma unroll
+      for (int ci = 0; ci < kChunk; ++ci) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[co][ci][0]);   // taps (0,0) (0,1) (0,2) (1,0)
+        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[co][ci][4]);   // taps (1,1) (1,2) (2,0) (2,1)
+        const float w22 = wsm[co][ci][8];
+        // (even, even): kh = 1, kw = 1
+        acc[ci][0] = fmaf(d00, w1.x, acc[ci][0]);
+        // (even, odd): kh = 1; kw = 0 -> ow = j + 1, kw = 2 -> ow = j
+        acc[ci][1] = fmaf(d01, w0.w, fmaf(d00, w1.y, acc[ci][1]));
+        // (odd, even): kw = 1; kh = 0 -> oh = i + 1, kh = 2 -> oh = i
+        acc[ci][2] = fmaf(d10, w0.y, fmaf(d00, w1.w, acc[ci][2]));
+        // (odd, odd): kh, kw in {0, 2}
+        acc[ci][3] = fmaf(d11, w0.x, fmaf(d10, w0.z, fmaf(d01, w1.z, fmaf(d00, w22, acc[ci][3]))));
+      }
+    }
+    if (ih < hin && iw < hin) {
+      float* o = dA + ((size_t)b * kC + ci0) * hin * hin;
+#pragma unroll
+      for (int ci = 0; ci < kChunk; ++ci) {
+        float* oc = o + (size_t)ci * hin * hin;
+        *reinterpret_cast<float2*>(&oc[(size_t)ih * hin + iw]) = make_float2(acc[ci][0], acc[ci][1]);
+        *reinterpret_cast<float2*>(&oc[(size_t)(ih + 1) * hin + iw]) = make_float2(acc[ci][2], acc[ci][3]);
+      }
     }
   }
 }
@@ -774,7 +780,7 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float
       // data gradient into dA (now sized for layer l-1's output == this layer's input)
       const int qt = cdiv(hout, kTile);
       // reads (y_l, dA_l), writes dA_{l-1} into the other buffer
-      conv_dgrad_kernel<<<dim3(qt * qt, cfg->B, kC / kChunk), 256, 0, st>>>(y, dA, aff, coef, L[l].w, dA_next, hin, hout, qt);
+      conv_dgrad_kernel<<<dim3(qt * qt, cfg->B), 256, 0, st>>>(y, dA, aff, coef, L[l].w, dA_next, hin, hout, qt);
       RN_LAUNCH_CHECK("conv_dgrad_kernel");
       float* t = dA; dA = dA_next; dA_next = t;
     }

@@ -23,7 +23,7 @@ __global__ void add_rowgroup_bias_kernel(float* __restrict__ V, const float* __r
 //   Qb[b, g] = b_qinj[g] + sum_j q[b, j] Wq[g, j];  U[b, o, g] = x[b, o, :] . W0c[g, :];  Vb = x . W0a[g, :] + beta0
 // One launch instead of three GEMMs and a bias pass; U / Vb rows are written once, fully coalesced.
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 rel_pre_fused_kernel(const float* __restrict__ x, const float* __restrict__ q, const float* __restrict__ w0, int fan0,
                      const float* __restrict__ wq, int ldq, const float* __restrict__ bq, const float* __restrict__ b0,
                      int q_at_layer0, int B, int n, int Q, int G, float* __restrict__ U, float* __restrict__ Vb,
@@ -32,7 +32,7 @@ rel_pre_fused_kernel(const float* __restrict__ x, const float* __restrict__ q, c
   float* wqT = pre_smem;                          // [Q][G + 1]
   float* xs = wqT + (size_t)Q * (G + 1);          // [n][K]
   float* qs = xs + (((size_t)n * K + 3) & ~(size_t)3);
-  const int g = threadIdx.x;
+  const int g = threadIdx.x % G, ohalf = threadIdx.x / G;      // two threads per feature: each takes half of the objects
   for (int base = 0; base < G * Q; base += 8 * blockDim.x) {      // 8 loads in flight per thread
     float t[8];
 #pragma unroll
@@ -73,9 +73,11 @@ rel_pre_fused_kernel(const float* __restrict__ x, const float* __restrict__ q, c
     float acc = bqv;
 #pragma unroll 8
     for (int j = 0; j < Q; ++j) acc = fmaf(qs[j], wqT[(size_t)j * (G + 1) + g], acc);
-    Qb[(size_t)b * G + g] = acc;
+    if (ohalf == 0) Qb[(size_t)b * G + g] = acc;
     const float vb = q_at_layer0 ? acc : b0v;
-    for (int o = 0; o < n; ++o) {
+    const int o_begin = ohalf * ((n + 1) / 2), o_end = ohalf == 0 ? (n + 1) / 2 : n;
+#pragma unroll 2
+    for (int o = o_begin; o < o_end; ++o) {
       float u = 0.f, v = vb;
 #pragma unroll
       for (int j = 0; j < K; j += 2) {
@@ -102,7 +104,7 @@ int relation_pre(const RelShape& s, const float* x, const float* q, const float*
     const float* wq = g_w[s.qinj] + (s.qinj == 0 ? 2 * s.k : s.G);
     const size_t smem = rel_pre_fused_smem(s);
     RN_CUDA(cudaFuncSetAttribute(rel_pre_fused_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rel_pre_fused_kernel<26><<<std::min(s.B, sm_count()), s.G, smem, st>>>(x, q, g_w[0], fan0, wq, s.fan_in(s.qinj),
+    rel_pre_fused_kernel<26><<<std::min(s.B, sm_count()), 2 * s.G, smem, st>>>(x, q, g_w[0], fan0, wq, s.fan_in(s.qinj),
                                                                           g_b[s.qinj], g_b[0], s.qinj == 0 ? 1 : 0, s.B,
                                                                           s.n, s.Q, s.G, pre.U, pre.Vb, pre.Qb);
     RN_LAUNCH_CHECK("rel_pre_fused_kernel");
@@ -152,7 +154,7 @@ static size_t layer0_bwd_smem() {
   return ((size_t)2 * kL0N * kL0Ld + (size_t)kL0G * 2 * kL0K + (size_t)kL0N * kL0K + (size_t)4 * kL0N * 28) * sizeof(float);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 layer0_bwd_fused_kernel(const float* __restrict__ dU, const float* __restrict__ dV, const float* __restrict__ x,
                         const float* __restrict__ w0, int fan0, int B, float* __restrict__ delta, float* __restrict__ dx,
                         float* __restrict__ part) {
@@ -161,18 +163,18 @@ layer0_bwd_fused_kernel(const float* __restrict__ dU, const float* __restrict__ 
   float* vs = us + kL0N * kL0Ld;                    // [64][257]
   float* ws = vs + kL0N * kL0Ld;                    // [256][52]: W0c | W0a rows
   float* xs = ws + kL0G * 2 * kL0K;                 // [64][26]
-  float* red = xs + kL0N * kL0K;                    // [4][64][28]
-  const int tid = threadIdx.x, g = tid;
-  for (int base = 0; base < kL0G * 2 * kL0K; base += 8 * 256) {
+  float* red = xs + kL0N * kL0K;                    // [4][64][28]; its head doubles as the delta0 exchange [256]
+  const int tid = threadIdx.x, g = tid & 255, ohalf = tid >> 8;    // phase A: two threads per feature (object halves)
+  for (int base = 0; base < kL0G * 2 * kL0K; base += 8 * 512) {
     float t[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * 256 + tid;
+      const int idx = base + u * 512 + tid;
       t[u] = idx < kL0G * 2 * kL0K ? w0[(size_t)(idx / (2 * kL0K)) * fan0 + idx % (2 * kL0K)] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * 256 + tid;
+      const int idx = base + u * 512 + tid;
       if (idx < kL0G * 2 * kL0K) ws[idx] = t[u];
     }
   }
@@ -185,7 +187,7 @@ layer0_bwd_fused_kernel(const float* __restrict__ dU, const float* __restrict__ 
     const float* du = dU + (size_t)b * kL0N * kL0G;
     const float* dv = dV + (size_t)b * kL0N * kL0G;
 #pragma unroll 1
-    for (int o0 = 0; o0 < kL0N; o0 += 8) {          // 16 coalesced row loads in flight per thread
+    for (int o0 = ohalf * 32; o0 < ohalf * 32 + 32; o0 += 8) {          // 16 coalesced row loads in flight per thread
       float tu[8], tv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -198,13 +200,13 @@ layer0_bwd_fused_kernel(const float* __restrict__ dU, const float* __restrict__ 
         vs[(o0 + i) * kL0Ld + g] = tv[i];
       }
     }
-    for (int i = tid; i < kL0N * kL0K; i += 256) xs[i] = x[(size_t)b * kL0N * kL0K + i];
+    for (int i = tid; i < kL0N * kL0K; i += 512) xs[i] = x[(size_t)b * kL0N * kL0K + i];
     __syncthreads();
 
     // ---- phase A ----
     float d0 = 0.f;
 #pragma unroll 2
-    for (int o = 0; o < kL0N; ++o) {
+    for (int o = ohalf * 32; o < ohalf * 32 + 32; ++o) {
       const float u = us[o * kL0Ld + g], v = vs[o * kL0Ld + g];
       d0 += v;
 #pragma unroll
@@ -216,44 +218,46 @@ layer0_bwd_fused_kernel(const float* __restrict__ dU, const float* __restrict__ 
         wa[j + 1] = fmaf(v, xv.y, wa[j + 1]);
       }
     }
-    delta[(size_t)b * kL0G + g] = d0;
-    db += d0;
+    if (ohalf == 1) red[g] = d0;                    // delta0 = sum over both object halves
+    __syncthreads();
+    if (ohalf == 0) {
+      d0 += red[g];
+      delta[(size_t)b * kL0G + g] = d0;
+      db += d0;
+    }
+    __syncthreads();                                // red is reused below
 
-    // ---- phase B ----
+    // ---- phase B: thread = (object o, K-quarter kq, half of the 26 outputs) ----
     {
-      const int o = tid & 63, kq = tid >> 6;
-      float acc[kL0K];
+      constexpr int JH = kL0K / 2;                  // 13
+      const int o = tid & 63, kq = (tid >> 6) & 3, j0 = (tid >> 8) * JH;
+      float acc[JH];
 #pragma unroll
-      for (int j = 0; j < kL0K; ++j) acc[j] = 0.f;
+      for (int j = 0; j < JH; ++j) acc[j] = 0.f;
 #pragma unroll 2
       for (int gg = kq * 64; gg < kq * 64 + 64; ++gg) {
         const float u = us[o * kL0Ld + gg], v = vs[o * kL0Ld + gg];
-        const float* wr = ws + gg * 2 * kL0K;         // warp-uniform: broadcast reads
+        const float* wr = ws + gg * 2 * kL0K + j0;         // warp-uniform: broadcast reads
 #pragma unroll
-        for (int j = 0; j < kL0K; j += 2) {
-          const float2 c2 = *reinterpret_cast<const float2*>(wr + j);
-          const float2 a2 = *reinterpret_cast<const float2*>(wr + kL0K + j);
-          acc[j] = fmaf(u, c2.x, fmaf(v, a2.x, acc[j]));
-          acc[j + 1] = fmaf(u, c2.y, fmaf(v, a2.y, acc[j + 1]));
-        }
+        for (int j = 0; j < JH; ++j) acc[j] = fmaf(u, wr[j], fmaf(v, wr[kL0K + j], acc[j]));
       }
 #pragma unroll
-      for (int j = 0; j < kL0K; ++j) red[(kq * kL0N + o) * 28 + j] = acc[j];
+      for (int j = 0; j < JH; ++j) red[(kq * kL0N + o) * 28 + j0 + j] = acc[j];
     }
     __syncthreads();
-    for (int i = tid; i < kL0N * kL0K; i += 256) {
+    for (int i = tid; i < kL0N * kL0K; i += 512) {
       const int o = i / kL0K, j = i % kL0K;
       dx[(size_t)b * kL0N * kL0K + i] = (red[(0 * kL0N + o) * 28 + j] + red[(1 * kL0N + o) * 28 + j]) +
                                         (red[(2 * kL0N + o) * 28 + j] + red[(3 * kL0N + o) * 28 + j]);
     }
   }
-  float* pr = part + (size_t)blockIdx.x * (kL0G * (2 * kL0K + 1));
+  float* pr = part + ((size_t)blockIdx.x * 2 + ohalf) * (kL0G * (2 * kL0K + 1));      // one partial per object half
 #pragma unroll
   for (int j = 0; j < kL0K; ++j) {
     pr[g * (2 * kL0K + 1) + j] = wc[j];
     pr[g * (2 * kL0K + 1) + kL0K + j] = wa[j];
   }
-  pr[g * (2 * kL0K + 1) + 2 * kL0K] = db;
+  pr[g * (2 * kL0K + 1) + 2 * kL0K] = db;            // zero for the second half (delta0 is folded into the first)
 }
 
 // dW0[g, 0:52] and db0[g] = fixed-order sums of the per-block partials
@@ -274,12 +278,12 @@ int relation_layer0_bwd(const RelShape& s, const float* x, const float* q, const
                         float* const* dg_b, float* ws, size_t ws_floats, cudaStream_t st) {
   const int fan0 = s.fan_in(0);
   const int nblk = std::min(s.B, sm_count());
-  if (s.k == kL0K && s.n == kL0N && s.G == kL0G && ws && ws_floats >= (size_t)nblk * kL0G * (2 * kL0K + 1)) {
+  if (s.k == kL0K && s.n == kL0N && s.G == kL0G && ws && ws_floats >= (size_t)2 * nblk * kL0G * (2 * kL0K + 1)) {
     const size_t smem = layer0_bwd_smem();
     RN_CUDA(cudaFuncSetAttribute(layer0_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layer0_bwd_fused_kernel<<<nblk, 256, smem, st>>>(dU, dV, x, g_w[0], fan0, s.B, delta, dx, ws);
+    layer0_bwd_fused_kernel<<<nblk, 512, smem, st>>>(dU, dV, x, g_w[0], fan0, s.B, delta, dx, ws);
     RN_LAUNCH_CHECK("layer0_bwd_fused_kernel");
-    layer0_bwd_reduce_kernel<<<cdiv(kL0G * (2 * kL0K + 1), 256), 256, 0, st>>>(ws, nblk, dg_w[0], fan0, dg_b[0]);
+    layer0_bwd_reduce_kernel<<<cdiv(kL0G * (2 * kL0K + 1), 256), 256, 0, st>>>(ws, 2 * nblk, dg_w[0], fan0, dg_b[0]);
     RN_LAUNCH_CHECK("layer0_bwd_reduce_kernel");
     if (s.qinj == 0) RN_TRY(relation_qinj_bwd(s, 0, q, g_w, delta, dq, dg_w, st));
     return RN_OK;
