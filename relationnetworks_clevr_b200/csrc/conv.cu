@@ -143,7 +143,7 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, 
   constexpr int NBUF = CIN > CC ? 2 : 1;
   constexpr int NCHUNK = CIN / CC;
   __shared__ __align__(16) float patch[NBUF][CC][kPatch][kPW];
-  __shared__ __align__(16) float wsm[NBUF][CC][kC][12];
+  __shared__ __align__(16) float wsm[NBUF][CC][9][kC];      // [ci][tap][co]: a thread's 6 channels are 3 adjacent pairs
   __shared__ float red[8][2 * kC];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -153,11 +153,12 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, 
   const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
   const float* inb = in + (size_t)b * CIN * hin * hin;
 
-  float acc[4][6];
+  // packed fp32x2 accumulators (FFMA2: two FMAs per issue slot on sm_100): acc[pixel][channel pair]
+  float2 acc[4][3];
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int c = 0; c < 6; ++c) acc[p][c] = 0.f;
+    for (int c = 0; c < 3; ++c) acc[p][c] = make_float2(0.f, 0.f);
 
   auto issue = [&](int k) {
     const int buf = k % NBUF, ci0 = k * CC;
@@ -165,7 +166,7 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, 
     for (int idx = tid; idx < CC * kC * 9; idx += 256) {
       const int ci = idx / (kC * 9), rem = idx % (kC * 9);
       const int co = rem / 9, t = rem % 9;
-      cp_async4(&wsm[buf][ci][co][t], w + ((size_t)co * CIN + ci0 + ci) * 9 + t, true);
+      cp_async4(&wsm[buf][ci][t][co], w + ((size_t)co * CIN + ci0 + ci) * 9 + t, true);
     }
   };
 
@@ -184,23 +185,24 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, 
 #pragma unroll
         for (int c = 0; c < 5; ++c) xv[r][c] = patch[buf][ci][4 * qy + r][4 * qx + c + kPO];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[buf][ci][cg * 6 + c][0]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[buf][ci][cg * 6 + c][4]);
-        const float w8 = wsm[buf][ci][cg * 6 + c][8];
-        const float wt[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w8};
+      for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-        for (int py = 0; py < 2; ++py)
+        for (int kw = 0; kw < 3; ++kw) {
+          const float* wr = &wsm[buf][ci][kh * 3 + kw][cg * 6];
+          const float2 w01 = *reinterpret_cast<const float2*>(wr);
+          const float2 w23 = *reinterpret_cast<const float2*>(wr + 2);
+          const float2 w45 = *reinterpret_cast<const float2*>(wr + 4);
 #pragma unroll
-          for (int px = 0; px < 2; ++px) {
-            float a = acc[py * 2 + px][c];
+          for (int py = 0; py < 2; ++py)
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-              for (int kw = 0; kw < 3; ++kw) a = fmaf(xv[2 * py + kh][2 * px + kw], wt[kh * 3 + kw], a);
-            acc[py * 2 + px][c] = a;
-          }
-      }
+            for (int px = 0; px < 2; ++px) {
+              const float x = xv[2 * py + kh][2 * px + kw];
+              const float2 xx = make_float2(x, x);
+              acc[py * 2 + px][0] = __ffma2_rn(xx, w01, acc[py * 2 + px][0]);
+              acc[py * 2 + px][1] = __ffma2_rn(xx, w23, acc[py * 2 + px][1]);
+              acc[py * 2 + px][2] = __ffma2_rn(xx, w45, acc[py * 2 + px][2]);
+            }
+        }
     }
   }
 
@@ -212,7 +214,8 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, 
   for (int c = 0; c < 6; ++c) {
     const int co = cg * 6 + c;
     const float bv = bias[co];
-    const float v00 = acc[0][c] + bv, v01 = acc[1][c] + bv, v10 = acc[2][c] + bv, v11 = acc[3][c] + bv;
+    const float v00 = (c & 1 ? acc[0][c >> 1].y : acc[0][c >> 1].x) + bv, v01 = (c & 1 ? acc[1][c >> 1].y : acc[1][c >> 1].x) + bv;
+    const float v10 = (c & 1 ? acc[2][c >> 1].y : acc[2][c >> 1].x) + bv, v11 = (c & 1 ? acc[3][c >> 1].y : acc[3][c >> 1].x) + bv;
     if (valid) {
       *reinterpret_cast<float2*>(&yb[((size_t)co * hout + oh) * hout + ow]) = make_float2(v00, v01);
       *reinterpret_cast<float2*>(&yb[((size_t)co * hout + oh + 1) * hout + ow]) = make_float2(v10, v11);
@@ -488,11 +491,11 @@ conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff
     __syncthreads();
     stage_patch<CC>(patch, inb, in_aff, ci0, ih0, iw0, hin, tid);
     __syncthreads();
-    float acc[6][9];
+    float2 acc2[3][9];           // packed (channel 2j, 2j+1) accumulators: FFMA2
 #pragma unroll
-    for (int j = 0; j < 6; ++j)
+    for (int j = 0; j < 3; ++j)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
+      for (int t = 0; t < 9; ++t) acc2[j][t] = make_float2(0.f, 0.f);
     if (lane_active) {
 #pragma unroll 2
       for (int p = pp; p < kTile * kTile; p += 8 * NSUB) {
@@ -503,15 +506,25 @@ conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) xv[kh * 3 + kw] = patch[ci][2 * py + kh][2 * px + kw + kPO];
-        float g[6];
+        float2 g2[3];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) g[j] = dys[(cg * 6 + j) * kDyLd + p];
+        for (int j = 0; j < 3; ++j) g2[j] = make_float2(dys[(cg * 6 + 2 * j) * kDyLd + p], dys[(cg * 6 + 2 * j + 1) * kDyLd + p]);
 #pragma unroll
-        for (int j = 0; j < 6; ++j)
+        for (int t = 0; t < 9; ++t) {
+          const float2 xx = make_float2(xv[t], xv[t]);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(g[j], xv[t], acc[j][t]);
+          for (int j = 0; j < 3; ++j) acc2[j][t] = __ffma2_rn(g2[j], xx, acc2[j][t]);
+        }
       }
     }
+    float acc[6][9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        acc[2 * j][t] = acc2[j][t].x;
+        acc[2 * j + 1][t] = acc2[j][t].y;
+      }
     if (NSUB == 2) {           // fold sub-partition 1 (lanes 12..23) into sub-partition 0 (lanes 0..11)
 #pragma unroll
       for (int j = 0; j < 6; ++j)
@@ -557,7 +570,7 @@ conv_dgrad_kernel(const float* __restrict__ yout, const float* __restrict__ dAou
                   const float* __restrict__ coef, const float* __restrict__ w, float* __restrict__ dA, int hin, int hout,
                   int tiles_x) {
   __shared__ __align__(16) float dys[kC][kTile + 1][kTile + 4];
-  __shared__ __align__(16) float wsm[kC][kChunk][12];
+  __shared__ __align__(16) float wsm[kC][9][kChunk];        // [co][tap][ci]: channel pairs adjacent (FFMA2)
   const int tid = threadIdx.x, tx = tid % kTile, ty = tid / kTile;
   const int b = blockIdx.y;
   const int q0y = (blockIdx.x / tiles_x) * kTile, q0x = (blockIdx.x % tiles_x) * kTile;   // quad == output coords
@@ -574,35 +587,53 @@ conv_dgrad_kernel(const float* __restrict__ yout, const float* __restrict__ dAou
     for (int idx = tid; idx < kC * kChunk * 9; idx += 256) {
       const int co = idx / (kChunk * 9), rem = idx % (kChunk * 9);
       const int ci = rem / 9, t = rem % 9;
-      wsm[co][ci][t] = w[((size_t)co * kC + ci0 + ci) * 9 + t];
+      wsm[co][t][ci] = w[((size_t)co * kC + ci0 + ci) * 9 + t];
     }
     __syncthreads();
     if (!warp_active) continue;
 
-    // quad (i, j) covers input pixels (2i, 2j), (2i, 2j+1), (2i+1, 2j), (2i+1, 2j+1)
-    float acc[kChunk][4];
+    // quad (i, j) covers input pixels (2i, 2j), (2i, 2j+1), (2i+1, 2j), (2i+1, 2j+1); accumulators packed over channel pairs
+    float2 acc2[kChunk / 2][4];
 #pragma unroll
-    for (int ci = 0; ci < kChunk; ++ci)
+    for (int c2 = 0; c2 < kChunk / 2; ++c2)
 #pragma unroll
-      for (int p = 0; p < 4; ++p) acc[ci][p] = 0.f;
+      for (int p = 0; p < 4; ++p) acc2[c2][p] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int co = 0; co < kC; ++co) {
       const float d00 = dys[co][ty][tx], d01 = dys[co][ty][tx + 1], d10 = dys[co][ty + 1][tx], d11 = dys[co][ty + 1][tx + 1];
+      const float2 e00 = make_float2(d00, d00), e01 = make_float2(d01, d01), e10 = make_float2(d10, d10), e11 = make_float2(d11, d11);
 #pragma unroll
-      for (int ci = 0; ci < kChunk; ++ci) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[co][ci][0]);   // taps (0,0) (0,1) (0,2) (1,0)
-        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[co][ci][4]);   // taps (1,1) (1,2) (2,0) (2,1)
-        const float w22 = wsm[co][ci][8];
-        // (even, even): kh = 1, kw = 1
-        acc[ci][0] = fmaf(d00, w1.x, acc[ci][0]);
-        // (even, odd): kh = 1; kw = 0 -> ow = j + 1, kw = 2 -> ow = j
-        acc[ci][1] = fmaf(d01, w0.w, fmaf(d00, w1.y, acc[ci][1]));
-        // (odd, even): kw = 1; kh = 0 -> oh = i + 1, kh = 2 -> oh = i
-        acc[ci][2] = fmaf(d10, w0.y, fmaf(d00, w1.w, acc[ci][2]));
-        // (odd, odd): kh, kw in {0, 2}
-        acc[ci][3] = fmaf(d11, w0.x, fmaf(d10, w0.z, fmaf(d01, w1.z, fmaf(d00, w22, acc[ci][3]))));
+      for (int h = 0; h < 2; ++h) {          // channel pairs (0,1),(2,3) then (4,5),(6,7): one LDS.128 per tap
+        float2 wt[9][2];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 v = *reinterpret_cast<const float4*>(&wsm[co][t][4 * h]);
+          wt[t][0] = make_float2(v.x, v.y);
+          wt[t][1] = make_float2(v.z, v.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          float2* a = acc2[2 * h + k];
+          // taps: 0 (0,0) 1 (0,1) 2 (0,2) 3 (1,0) 4 (1,1) 5 (1,2) 6 (2,0) 7 (2,1) 8 (2,2)
+          // (even, even): kh = 1, kw = 1
+          a[0] = __ffma2_rn(e00, wt[4][k], a[0]);
+          // (even, odd): kh = 1; kw = 0 -> ow = j + 1, kw = 2 -> ow = j
+          a[1] = __ffma2_rn(e01, wt[3][k], __ffma2_rn(e00, wt[5][k], a[1]));
+          // (odd, even): kw = 1; kh = 0 -> oh = i + 1, kh = 2 -> oh = i
+          a[2] = __ffma2_rn(e10, wt[1][k], __ffma2_rn(e00, wt[7][k], a[2]));
+          // (odd, odd): kh, kw in {0, 2}
+          a[3] = __ffma2_rn(e11, wt[0][k], __ffma2_rn(e10, wt[2][k], __ffma2_rn(e01, wt[6][k], __ffma2_rn(e00, wt[8][k], a[3]))));
+        }
       }
     }
+    float acc[kChunk][4];
+#pragma unroll
+    for (int c2 = 0; c2 < kChunk / 2; ++c2)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        acc[2 * c2][p] = acc2[c2][p].x;
+        acc[2 * c2 + 1][p] = acc2[c2][p].y;
+      }
     if (ih < hin && iw < hin) {
       float* o = dA + ((size_t)b * kC + ci0) * hin * hin;
 #pragma unroll
