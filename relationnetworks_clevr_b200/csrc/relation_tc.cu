@@ -116,6 +116,7 @@ struct ChainParams {
   __half* dZ;                      // [tiles][4] x 64 KB images dZ1..dZ4 (scaled by S)
   int dbg;                         // timing ablations (RN_B200_DBG; results are garbage when nonzero)
   int skip_dz4_image;              // dgrad: the weight-gradient kernel regenerates dZ4 from the sign bits
+  int sched;                       // MMA job order (for_each_chain_job)
 };
 
 struct Bars {
@@ -338,6 +339,41 @@ __device__ long long g_chain_prof[160][16];
 #define PROF_T0() long long _t0 = 0; if (prof) _t0 = clock64();
 #define PROF_ACC(i) if (prof) { const long long _t1 = clock64(); pacc[i] += _t1 - _t0; _t0 = _t1; }
 
+// Static MMA job order shared by the weight producer and the MMA issuer (the epilogue warps are driven by barriers only).
+// sched 0: round r = [s0 L1, s1 L1, s0 L2, s1 L2, s0 L3, s1 L3]  (strict alternation)
+// sched 1: round r = [s0 L1, s1 L3 (previous tile), s0 L2, s0 L3, s1 L1, s1 L2]: every slot gets TWO MMA phases of the
+//          other slot between its last layer and the first layer of its next tile, which covers the tile boundary
+//          (pair-sum epilogue + operand generation, ~14 k cycles) instead of one (6.8 k), at the price of one
+//          back-to-back pair per slot whose gap is a 4 k mid-layer epilogue.  Measured at B=640: 2.25 / 2.87 / 1.77 ms
+//          (train forward / backward / eval forward) against 2.23 / 2.91 / 1.61 ms for sched 0, which stays the
+//          default (RN_B200_SCHED).
+template <typename F>
+__device__ __forceinline__ void for_each_chain_job(int my_tiles, int sched, F&& f) {
+  const int rounds = (my_tiles + 1) / 2;
+  if (sched == 0) {
+    for (int r = 0; r < rounds; ++r) {
+      const int nslots = (2 * r + 1 < my_tiles) ? 2 : 1;
+      for (int layer = 0; layer < kTcLayers; ++layer)
+        for (int s = 0; s < nslots; ++s) f(s, layer);
+    }
+    return;
+  }
+  bool pending1 = false;                 // slot 1 still owes the last layer of its previous tile
+  for (int r = 0; r < rounds; ++r) {
+    const bool has1 = 2 * r + 1 < my_tiles;
+    f(0, 0);
+    if (pending1) f(1, 2);
+    f(0, 1);
+    f(0, 2);
+    if (has1) {
+      f(1, 0);
+      f(1, 1);
+    }
+    pending1 = has1;
+  }
+  if (pending1) f(1, 2);
+}
+
 // GEN = true (single-CTA form only): a fourth warpgroup generates the layer-1 operand of each slot's NEXT tile as
 // soon as the slot's last MMA has released the A buffer, concurrently with the slot's own last-layer epilogue (which
 // only reads TMEM), instead of the epilogue warps doing both back to back on the slot's critical path.
@@ -390,24 +426,20 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
     if (lane == 0) {
       // ================= weight producer =================
       uint32_t stage = 0, phase = 0;
-      for (int r = 0; 2 * r < my_tiles; ++r) {
-        const int nslots = (2 * r + 1 < my_tiles) ? 2 : 1;
-        for (int layer = 0; layer < kTcLayers; ++layer) {
-          const int img_layer = MODE == kDgrad ? kTcLayers - 1 - layer : layer;    // dgrad walks W3^T, W2^T, W1^T
-          for (int s = 0; s < nslots; ++s)
-            for (int pass = 0; pass < ((p.dbg & 4) ? 0 : (p.dbg & 1) ? 1 : p.passes); ++pass)
-              for (int kc = 0; kc < kNKC; ++kc) {
-                mbar_wait(smem_u32(&bars->w_empty[stage]), phase ^ 1);
-                const uint32_t full = smem_u32(&bars->w_full[stage]);
-                mbar_expect_tx(full, STAGE_BYTES);
-                // pair mode: this CTA's N-half = rows [128*rank, 128*rank + 128) = the rank-th 16 KB of the chunk image
-                const char* src = reinterpret_cast<const char*>(p.wpack) + ((size_t)(img_layer * 2 + pass) * kNKC + kc) * kWChunk +
-                                  (CTA2 ? rank * kWHalf : 0);
-                bulk_g2s(smem_u32(smem + kSmemW + stage * STAGE_BYTES), src, STAGE_BYTES, full);
-                if (++stage == NST) { stage = 0; phase ^= 1; }
-              }
-        }
-      }
+      for_each_chain_job(my_tiles, CTA2 ? 0 : p.sched, [&](int, int layer) {
+        const int img_layer = MODE == kDgrad ? kTcLayers - 1 - layer : layer;    // dgrad walks W3^T, W2^T, W1^T
+        for (int pass = 0; pass < ((p.dbg & 4) ? 0 : (p.dbg & 1) ? 1 : p.passes); ++pass)
+          for (int kc = 0; kc < kNKC; ++kc) {
+            mbar_wait(smem_u32(&bars->w_empty[stage]), phase ^ 1);
+            const uint32_t full = smem_u32(&bars->w_full[stage]);
+            mbar_expect_tx(full, STAGE_BYTES);
+            // pair mode: this CTA's N-half = rows [128*rank, 128*rank + 128) = the rank-th 16 KB of the chunk image
+            const char* src = reinterpret_cast<const char*>(p.wpack) + ((size_t)(img_layer * 2 + pass) * kNKC + kc) * kWChunk +
+                              (CTA2 ? rank * kWHalf : 0);
+            bulk_g2s(smem_u32(smem + kSmemW + stage * STAGE_BYTES), src, STAGE_BYTES, full);
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+          }
+      });
     }
   } else if (warp == 1) {
     if (lane == 0 && (!CTA2 || rank == 0)) {
@@ -417,10 +449,7 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
       const bool prof = (p.dbg & 8) != 0;
       long long pacc[4] = {0, 0, 0, 0};
       PROF_T0();
-      for (int r = 0; 2 * r < my_tiles; ++r) {
-        const int nslots = (2 * r + 1 < my_tiles) ? 2 : 1;
-        for (int layer = 0; layer < kTcLayers; ++layer)
-          for (int s = 0; s < nslots; ++s) {
+      for_each_chain_job(my_tiles, CTA2 ? 0 : p.sched, [&](int s, int) {
             if (CTA2) mbar_wait_cluster(smem_u32(&bars->a_full[s]), a_phase[s]);
             else mbar_wait(smem_u32(&bars->a_full[s]), a_phase[s]);
             a_phase[s] ^= 1;
@@ -455,8 +484,7 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
             if (CTA2) mma_commit_2cta(smem_u32(&bars->acc_full[s]), 3);
             else mma_commit(smem_u32(&bars->acc_full[s]));
             PROF_ACC(2);
-          }
-      }
+      });
       if (prof) for (int i = 0; i < 3; ++i) g_chain_prof[blockIdx.x][8 + i] = pacc[i];
     } else if (CTA2 && lane == 0) {
       // ================= peer CTA relay: tell the leader when this CTA's half of each chunk has landed =================
@@ -1203,6 +1231,10 @@ extern "C" int rn_debug_chain_profile(long long* out) {   // 160 x 16 counters o
   return cudaMemcpyFromSymbol(out, rn::g_chain_prof, sizeof(rn::g_chain_prof)) == cudaSuccess ? 0 : 1;
 }
 namespace rn {
+static int chain_sched() {
+  static const int v = []() { const char* e = getenv("RN_B200_SCHED"); return e ? atoi(e) : 0; }();
+  return v;
+}
 static int chain_dbg() {
   static const int v = []() { const char* e = getenv("RN_B200_DBG"); return e ? atoi(e) : 0; }();
   return v;
@@ -1262,6 +1294,7 @@ int tc_relation_fwd(const RelShape& s, int precision, bool training, const float
 
   ChainParams p = {};
   p.dbg = chain_dbg();
+  p.sched = chain_sched();
   p.U = sv.pre.U;
   p.Vb = sv.pre.Vb;
   for (int l = 0; l < kTcLayers; ++l) {
@@ -1311,6 +1344,7 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
   // data gradient chain: dZ4 -> dZ3 -> dZ2 -> dZ1 (images to HBM), column sums of dZ2..dZ4
   ChainParams p = {};
   p.dbg = chain_dbg();
+  p.sched = chain_sched();
   p.wpack = ws.wpackT;
   p.n = s.n;
   p.tiles_per_sample = tps;
