@@ -171,13 +171,22 @@ __host__ __device__ constexpr int mask_pos(int e) { return (e >> 1) + 16 * (e & 
 // Warp `q` (0..3) of the warpgroup owns rows [32q, 32q+32).  Lane mapping: 4 rows x 8 sixteen-byte groups per
 // step -> 256-byte coalesced reads of U, conflict-free STS.  M1 sign bits use a lane-local layout
 // word j = (col % 64) / 8, bit = (col / 64) * 8 + col % 8.
-template <bool SAVE>
-__device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
+template <bool SAVE, bool ONE_A>
+__device__ __forceinline__ void generate_h1_rows(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
   const int b = tile / p.tiles_per_sample;
   const int p0 = (tile % p.tiles_per_sample) * kTileM;
   const float* Ub = p.U + (size_t)b * p.n * kG;
   const float* Vb = p.Vb + (size_t)b * p.n * kG;
   const int sub = lane >> 3, j = lane & 7;
+  float4 vr[ONE_A ? kNKC : 1][2];             // ONE_A: the tile lies inside one value of `a` (n % 128 == 0): its Vb row stays in registers
+  if (ONE_A) {
+    const float4* vp = reinterpret_cast<const float4*>(Vb + (size_t)(p0 / p.n) * kG + j * 8);
+#pragma unroll
+    for (int kc = 0; kc < kNKC; ++kc) {
+      vr[kc][0] = __ldg(vp + kc * 16);
+      vr[kc][1] = __ldg(vp + kc * 16 + 1);
+    }
+  }
 #pragma unroll 2
   for (int g = 0; g < 8; ++g) {
     const int row = q * 32 + g * 4 + sub;
@@ -189,7 +198,7 @@ __device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char
 #pragma unroll
     for (int kc = 0; kc < kNKC; ++kc) {
       const float4 u0 = __ldg(up + kc * 16), u1 = __ldg(up + kc * 16 + 1);
-      const float4 v0 = __ldg(vp + kc * 16), v1 = __ldg(vp + kc * 16 + 1);
+      const float4 v0 = ONE_A ? vr[ONE_A ? kc : 0][0] : __ldg(vp + kc * 16), v1 = ONE_A ? vr[ONE_A ? kc : 0][1] : __ldg(vp + kc * 16 + 1);
       const float h[8] = {u0.x + v0.x, u0.y + v0.y, u0.z + v0.z, u0.w + v0.w, u1.x + v1.x, u1.y + v1.y, u1.z + v1.z, u1.w + v1.w};
       uint4 o;
       o.x = pack_relu_half2(h[0], h[1]);
@@ -206,6 +215,12 @@ __device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char
     }
     if (SAVE) p.masks[((size_t)tile * kTileM + row) * 8 + j] = bits;      // masks[0] = M1
   }
+}
+
+template <bool SAVE>
+__device__ __forceinline__ void generate_h1(const ChainParams& p, int tile, char* a_tile, int q, int lane) {
+  if (p.n % kTileM == 0) generate_h1_rows<SAVE, true>(p, tile, a_tile, q, lane);
+  else generate_h1_rows<SAVE, false>(p, tile, a_tile, q, lane);
 }
 
 // n == 64 fast path (the 8x8 grid): a tile is 2 values of `a` x all 64 values of `c`, so U[c] is read ONCE for both

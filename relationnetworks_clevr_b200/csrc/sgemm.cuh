@@ -49,11 +49,12 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long long lda, co
   const int k_end = min(K, k_begin + k_chunk);
   const int tx = tid % 16, ty = tid / 16;
 
-  float acc[TM][TN];
+  // packed fp32x2 accumulators over column pairs (FFMA2: two FMAs per issue slot on sm_100)
+  float2 acc2[TM][TN / 2];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN / 2; ++j) acc2[i][j] = make_float2(0.f, 0.f);
 
   float ra[LA], rb[LB];
 
@@ -123,13 +124,23 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long long lda, co
           *reinterpret_cast<float2*>(&b[0]) = *reinterpret_cast<const float2*>(&Bs[kk][tx * 2]);
         }
 #pragma unroll
-        for (int i = 0; i < TM; ++i)
+        for (int i = 0; i < TM; ++i) {
+          const float2 aa = make_float2(a[i], a[i]);
 #pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < TN / 2; ++j) acc2[i][j] = __ffma2_rn(aa, make_float2(b[2 * j], b[2 * j + 1]), acc2[i][j]);
+        }
       }
       __syncthreads();
     }
   }
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN / 2; ++j) {
+      acc[i][2 * j] = acc2[i][j].x;
+      acc[i][2 * j + 1] = acc2[i][j].y;
+    }
 
   float* Cz = C + (long long)blockIdx.z * split_stride;
   const bool raw = split_stride != 0;   // split-K partials: no epilogue here
