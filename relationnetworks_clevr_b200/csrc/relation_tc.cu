@@ -116,6 +116,7 @@ struct ChainParams {
   __half* dZ;                      // [tiles][4] x 64 KB images dZ1..dZ4 (scaled by S)
   int dbg;                         // timing ablations (RN_B200_DBG; results are garbage when nonzero)
   int skip_dz4_image;              // dgrad: the weight-gradient kernel regenerates dZ4 from the sign bits
+  int skip_h1_image;               // training forward: the layer-1 weight-gradient kernel regenerates H1 from U / V'
   int sched;                       // MMA job order (for_each_chain_job)
 };
 
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
         else if (p.n == 64) generate_h1_n64<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
         else generate_h1<MODE == kFwdTrain>(p, tile, a_tile, q, lane);
         fence_proxy_async_smem();
-        if (MODE == kFwdTrain) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile);
+        if (MODE == kFwdTrain && !p.skip_h1_image) store_image(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile);
         if (MODE == kDgrad && !p.skip_dz4_image) store_image(reinterpret_cast<char*>(p.dZ) + ((size_t)tile * 4 + 3) * kATile);
         arrive_a_full();
       }
@@ -807,7 +808,11 @@ struct WgradParams {
   int num_tiles;
   // regen != 0 (layer 3): the dZ operand is dZ4 = S * dxg .* (Z4 > 0), regenerated here from the sign bits (32 B per
   // row instead of a 512 B image row that the dgrad kernel would have to write and this kernel read back)
+  // regen == 2 (layer 1, n == 64): the H operand is H1 = relu(U[c] + V'[a]), regenerated here from U / V' (L2-resident,
+  // read once per tile for both halves) instead of a tile image the forward kernel would have to write and this one read
   int regen;
+  const float* U;          // [B, 64, 256]
+  const float* Vb;         // [B, 64, 256]
   const uint32_t* masks4;  // [tiles][128][8]
   const float* dxg;        // [B, 256]
   const float* scale;
@@ -831,7 +836,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradPa
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kWgStages; ++s) {
       mbar_init(smem_u32(&bars->full[s]), p.regen ? 1 + 4 : 1);   // producer (+ the 4 generating warps)
-      mbar_init(smem_u32(&bars->empty[s]), p.regen ? 1 : 1 + 4);      // MMA commit (+ the 4 column-sum warps)
+      mbar_init(smem_u32(&bars->empty[s]), p.regen == 1 ? 1 : 1 + 4);      // MMA commit (+ the 4 column-sum warps)
     }
     mbar_init(smem_u32(&bars->done), 1);
     fence_mbar_init();
@@ -854,8 +859,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradPa
           const uint32_t dst = smem_u32(smem + stage * kWgStageBytes);
 #pragma unroll
           for (int c = 0; c < kNKC; ++c) {      // rows [64*half, 64*half+64) of column chunk c: 8 KB contiguous
-            if (!p.regen) bulk_g2s(dst + c * 8192, p.dZ + tile * p.dz_stride + c * kAChunk + half * 8192, 8192, full);
-            bulk_g2s(dst + 32768 + c * 8192, p.H + tile * p.h_stride + c * kAChunk + half * 8192, 8192, full);
+            if (p.regen != 1) bulk_g2s(dst + c * 8192, p.dZ + tile * p.dz_stride + c * kAChunk + half * 8192, 8192, full);
+            if (p.regen != 2) bulk_g2s(dst + 32768 + c * 8192, p.H + tile * p.h_stride + c * kAChunk + half * 8192, 8192, full);
           }
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
@@ -894,7 +899,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradPa
       const uint32_t grp = (uint32_t)((col & 63) >> 3);
       uint32_t stage = 0, phase = 0;
       float2 acc = make_float2(0.f, 0.f);
-      if (p.regen) {
+      if (p.regen == 1) {
         // Regenerate every dZ4 half tile into the stage's A slot: warp gw takes rows [16*gw, 16*gw + 16), lane owns columns
         // [8*lane, 8*lane + 8) (chunk lane / 8, group lane % 8).  Mask words and dxg of the NEXT half tile are loaded while
         // this one is generated.  Column sums (bias gradient) come from per-column bit counts: count * S*dxg.
@@ -962,6 +967,84 @@ __global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradPa
 #pragma unroll
           for (int r = 0; r < 16; ++r) w[r] = wn[r];
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+      } else if (p.regen == 2) {
+        // Regenerate the H1 halves of every tile into the B slots of TWO consecutive stages (rows (a0, c) and (a1, c)):
+        // warp gw takes c in [16*gw, 16*gw + 16), lane owns columns [4*lane, +4) and [128 + 4*lane, +4).  The tile's U
+        // rows live in registers; the NEXT tile's rows are loaded right after this tile is generated and land while the
+        // column sums of the staged dZ halves are taken.
+        const int gw = warp - 2;
+        auto tile_of = [&](int it) { return (size_t)blockIdx.x + (size_t)it * gridDim.x; };
+        float4 uu[16][2], vv[2][2];
+        auto load_uv = [&](int it) {
+          const size_t tile = tile_of(it);
+          const size_t b = tile / p.tiles_per_sample;
+          const int a0 = (int)(tile % p.tiles_per_sample) * 2;
+          const float* Ub = p.U + (b * 64 + gw * 16) * kG + 4 * lane;
+          const float* Vb = p.Vb + (b * 64 + a0) * kG + 4 * lane;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            uu[r][0] = __ldg(reinterpret_cast<const float4*>(Ub + (size_t)r * kG));
+            uu[r][1] = __ldg(reinterpret_cast<const float4*>(Ub + (size_t)r * kG + 128));
+          }
+#pragma unroll
+          for (int ai = 0; ai < 2; ++ai) {
+            vv[ai][0] = __ldg(reinterpret_cast<const float4*>(Vb + ai * kG));
+            vv[ai][1] = __ldg(reinterpret_cast<const float4*>(Vb + ai * kG + 128));
+          }
+        };
+        auto colsum_half = [&](uint32_t stg, uint32_t ph, int i) {
+          mbar_wait(smem_u32(&bars->full[stg]), ph);
+          const char* st = smem + stg * kWgStageBytes + coff;
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r) {
+            const __half2 h = *reinterpret_cast<const __half2*>(st + (r >> 3) * 1024 + (r & 7) * 128 + ((grp ^ (uint32_t)(r & 7)) << 4));
+            const float2 f = __half22float2(h);
+            acc.x += f.x;
+            acc.y += f.y;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->empty[stg]));
+          if (i & 1) {
+            *reinterpret_cast<float2*>(p.colpart + tile_of(i >> 1) * kG + col) = acc;
+            acc = make_float2(0.f, 0.f);
+          }
+        };
+        if (my_tiles > 0) load_uv(0);
+        const uint32_t goff = (uint32_t)(lane >> 4) * 8192u + (uint32_t)((4 * lane) & 7) * 2u;      // chunk + byte inside the 16-byte group
+        const int ggrp = ((4 * lane) & 63) >> 3;
+        for (int it = 0; it < my_tiles; ++it) {
+          const uint32_t s_a = stage, ph_a = phase;
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+          const uint32_t s_b = stage, ph_b = phase;
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+          mbar_wait(smem_u32(&bars->empty[s_a]), ph_a ^ 1);
+          mbar_wait(smem_u32(&bars->empty[s_b]), ph_b ^ 1);
+#pragma unroll
+          for (int ai = 0; ai < 2; ++ai) {
+            char* dst = smem + (ai == 0 ? s_a : s_b) * kWgStageBytes + 32768 + goff;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const int c = gw * 16 + r;
+              const uint32_t off = (uint32_t)((c >> 3) * 1024 + (c & 7) * 128 + (((ggrp ^ (c & 7)) & 7) << 4));
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint2 o;
+                o.x = pack_relu_half2(uu[r][h].x + vv[ai][h].x, uu[r][h].y + vv[ai][h].y);
+                o.y = pack_relu_half2(uu[r][h].z + vv[ai][h].z, uu[r][h].w + vv[ai][h].w);
+                *reinterpret_cast<uint2*>(dst + h * 2 * 8192 + off) = o;
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(smem_u32(&bars->full[s_a]));
+            mbar_arrive(smem_u32(&bars->full[s_b]));
+          }
+          if (it + 1 < my_tiles) load_uv(it + 1);
+          colsum_half(s_a, ph_a, 2 * it);
+          colsum_half(s_b, ph_b, 2 * it + 1);
         }
       } else {
       for (int i = 0; i < 2 * my_tiles; ++i) {
@@ -1246,6 +1329,13 @@ extern "C" int rn_debug_chain_profile(long long* out) {   // 160 x 16 counters o
   return cudaMemcpyFromSymbol(out, rn::g_chain_prof, sizeof(rn::g_chain_prof)) == cudaSuccess ? 0 : 1;
 }
 namespace rn {
+// H1 is regenerated inside the layer-1 weight-gradient kernel (8x8 grid only; RN_B200_REGEN_H1=0 streams its image like
+// H2 / H3; the generator-warpgroup form always stores it).  Forward and backward must agree.
+static bool tc_regen_h1(const RelShape& s) {
+  static const bool on = []() { const char* e = getenv("RN_B200_REGEN_H1"); return !(e && e[0] == '0'); }();
+  static const int gen_env = []() { const char* e = getenv("RN_B200_GENWG"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+  return on && gen_env != 1 && s.n == 64;
+}
 static int chain_sched() {
   static const int v = []() { const char* e = getenv("RN_B200_SCHED"); return e ? atoi(e) : 0; }();
   return v;
@@ -1324,6 +1414,7 @@ int tc_relation_fwd(const RelShape& s, int precision, bool training, const float
   p.wpack = sv.wpack;
   p.xg_part = static_cast<float*>(scratch);
   p.saveH = sv.saveH;
+  p.skip_h1_image = (training && tc_regen_h1(s)) ? 1 : 0;
   p.masks = sv.masks;
   p.n = s.n;
   p.tiles_per_sample = (int)(s.pairs / kTileM);
@@ -1390,7 +1481,9 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
     wp.partial = ws.partial;
     wp.colpart = ws.colpart + (size_t)(l - 1) * tiles * kG;
     wp.num_tiles = tiles;
-    wp.regen = (l == kTcLayers && p.skip_dz4_image) ? 1 : 0;
+    wp.regen = (l == kTcLayers && p.skip_dz4_image) ? 1 : (l == 1 && tc_regen_h1(s)) ? 2 : 0;
+    wp.U = sv.pre.U;
+    wp.Vb = sv.pre.Vb;
     wp.masks4 = sv.masks + (size_t)3 * tiles * kTileM * 8;
     wp.dxg = dxg;
     wp.scale = ws.scale;

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "generator_warpgroup_everywhere": {"RN_B200_GENWG": "1"},
     "classic_form_everywhere": {"RN_B200_GENWG": "0"},
-    "stored_dz4_two_pass_dgrad": {"RN_B200_REGEN_DZ4": "0", "RN_B200_DGRAD_PASSES": "2"},
+    "stored_dz4_h1_two_pass_dgrad": {"RN_B200_REGEN_DZ4": "0", "RN_B200_REGEN_H1": "0", "RN_B200_DGRAD_PASSES": "2"},
     "boundary_covering_job_order": {"RN_B200_SCHED": "1"},
     "text_encoder_on_main_stream": {"RN_B200_TEXT_STREAM": "0"},
 }
