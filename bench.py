@@ -222,7 +222,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL's own log (version banner, warnings) goes to stderr
+        # keep stdout to the one JSON line: no NCCL version banner unless the caller asked for a verbose NCCL log
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE", "ABORT"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.lib().rn_device_check(local_rank), "rn_device_check")
