@@ -1,7 +1,8 @@
 // relation_tc.cu -- tcgen05 / TMEM implementation of g-MLP layers 1..3 for G == 256 (original-fp, ir-fp and
 // the grid sweep).  See DESIGN.md "Kernels" for the pipeline description.
 //
-// Forward kernel rn_g_fwd_kernel (persistent, one CTA per SM, 384 threads):
+// Chain kernel rn_g_chain_kernel<MODE> (training forward / eval forward / data gradient share one skeleton;
+// persistent, one CTA per SM, 384 threads -- 512 with the optional generator warpgroup, see the GEN template flag):
 //   warp 0      weight producer: streams pre-swizzled fp16 weight chunks (32 KB = 256 out x 64 in) from L2 into a
 //               3-stage shared-memory ring with cp.async.bulk (TMA engine) + mbarrier complete_tx
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma M128 x N256 x K16 (kind::f16, fp32 accumulate in
@@ -12,7 +13,13 @@
 //               then per layer: tcgen05.ld accumulator -> +bias -> ReLU -> fp16 -> next layer's A operand in smem
 //               (activations never leave the SM); last layer: ReLU + warp-shuffle column sums (the pair-sum).
 //   Two tile slots ping-pong so one slot's epilogue overlaps the other slot's MMAs.
-// Precision: A operands fp16; weights W = W_hi + W_lo (two fp16 MMAs per K-step, "parity") or W_hi only ("fast").
+// Training streams the fp16 operand images H2, H3 / dZ1..dZ3 and the ReLU sign bits to HBM for the weight-gradient
+// kernel rn_g_wgrad_kernel (256x256 fp32 accumulator resident in TMEM, images read back as MN-major operands), which
+// REGENERATES H1 (from U / V') and dZ4 (from the sign bits) instead of reading images of them.
+// Precision: A operands fp16; weights W = W_hi + W_lo (two fp16 MMAs per K-step, "parity" forward) or W_hi only
+// ("fast", and the data gradient by default).
+// Diagnostics: RN_B200_DBG bit 0/1/2 = timing ablations (half the weight traffic / no epilogue arithmetic / no weight
+// streaming; results are garbage), bit 3 = in-kernel phase cycle counters read by tests/diag_tc_prof.py.
 #include "relation.cuh"
 #include "tc_ptx.cuh"
 
