@@ -1042,12 +1042,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) rn_g_wgrad_kernel(const WgradPa
                 *reinterpret_cast<uint2*>(dst + h * 2 * 8192 + off) = o;
               }
             }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(smem_u32(&bars->full[s_a]));
-            mbar_arrive(smem_u32(&bars->full[s_b]));
+            fence_proxy_async_smem();          // publish this half at once: its MMAs start while the other half is generated
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->full[ai == 0 ? s_a : s_b]));
           }
           if (it + 1 < my_tiles) load_uv(it + 1);
           colsum_half(s_a, ph_a, 2 * it);
