@@ -366,11 +366,11 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None,
                          # DRAM bytes of one forward+backward launch pair at B=640 (parity mode), from the committed ncu
-                         # capture profiles/r01b_chain_wgrad_ncu_full.txt: chain fwd 4.47 GB + dgrad 4.30 GB + wgrad
-                         # 2.72 + 2.72 + 1.45 GB (+ dZ1 reduce 1.34 GB).  Far above the ~6 MB algorithmic bytes by design:
-                         # training streams fp16 tile images (H1..H3, dZ1..dZ3) through HBM for the weight-gradient GEMMs
+                         # capture profiles/r01c_chain_wgrad_ncu_full.txt: chain fwd 3.13 GB + dgrad 4.30 GB + wgrad
+                         # 1.45 + 2.71 + 1.45 GB (+ dZ1 reduce 1.34 GB).  Far above the ~6 MB algorithmic bytes by design:
+                         # training streams fp16 tile images (H2, H3, dZ1..dZ3) through HBM for the weight-gradient GEMMs
                          # (DESIGN.md section 4).
-                         "traffic": 17.0e9 if (precision == "parity" and B == 640) else None,
+                         "traffic": 14.4e9 if (precision == "parity" and B == 640) else None,
                          "kernel": "g-MLP (rn_relation_fwd + rn_relation_bwd launches)",
                          "relation_fwd_ms": fwd_ms, "relation_bwd_ms": bwd_ms,
                          "algorithmic_flop_per_launch_pair": G_FLOP_TRAIN * B, "peak_source": peaks["source"] + " (sustained bf16)"},
