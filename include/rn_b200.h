@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RN_ABI_VERSION 1
+#define RN_ABI_VERSION 2
 
 /* error codes */
 #define RN_OK 0
@@ -39,8 +39,15 @@ extern "C" {
 
 /* arithmetic of the g-MLP layers 1..L-1 (layer 0 is always fp32) */
 #define RN_PRECISION_FP32 0    /* fp32 SIMT kernels, any shape; on-device yardstick                 */
-#define RN_PRECISION_PARITY 1  /* tcgen05: fp16 activations x (W_hi + W_lo) fp16 split, fp32 accum  */
+#define RN_PRECISION_PARITY 1  /* tcgen05, fp32-level: (A_hi + A_lo) x (W_hi + W_lo) fp16 splits, fp32 accum.
+                                * Training forward: 3 MMA passes per K-step (A_hi W_hi + A_lo W_hi + A_hi W_lo, A_lo
+                                * read from tensor memory) so the ReLU masks the backward uses agree with an fp32
+                                * evaluation; eval forward: 2 passes (A_hi only, measured 2e-6..9e-5 on log-probs). */
 #define RN_PRECISION_FAST 2    /* tcgen05: fp16 activations x fp16 weights, one pass, fp32 accum    */
+
+/* rn_relation_cfg.flags (0 = defaults).  Forward and backward of one step must use the same flags. */
+#define RN_REL_FLAG_FWD_2PASS 1u    /* PARITY training forward with fp16 activations only (the round-1 kernel) */
+#define RN_REL_FLAG_DGRAD_2PASS 2u  /* data gradient with W_hi + W_lo instead of W_hi                          */
 
 #define RN_MAX_G_LAYERS 8
 
@@ -56,6 +63,7 @@ typedef struct rn_relation_cfg {
   int32_t qinj;       /* hyp["question_injection_position"], 0 <= qinj < L                 */
   int32_t precision;  /* RN_PRECISION_*                                                    */
   int32_t training;   /* 1: keep what rn_relation_bwd needs in `saved`                     */
+  uint32_t flags;     /* RN_REL_FLAG_*                                                     */
 } rn_relation_cfg;
 
 int rn_abi_version(void);

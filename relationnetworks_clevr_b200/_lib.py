@@ -15,13 +15,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librn_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-RN_ABI_VERSION = 1
+RN_ABI_VERSION = 2
 PRECISION = {"fp32": 0, "parity": 1, "fast": 2}
 MAX_G_LAYERS = 8
 
 
 class RelationCfg(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("B", "n", "k", "Q", "G", "L", "qinj", "precision", "training")]
+    _fields_ = [(n, C.c_int32) for n in ("B", "n", "k", "Q", "G", "L", "qinj", "precision", "training")] + [("flags", C.c_uint32)]
 
 
 class FCfg(C.Structure):

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(512)
 rel_pre_fused_kernel(const float* __restrict__ x, const float* __restrict__ q, const float* __restrict__ w0, int fan0,
                      const float* __restrict__ wq, int ldq, const float* __restrict__ bq, const float* __restrict__ b0,
                      int q_at_layer0, int B, int n, int Q, int G, float* __restrict__ U, float* __restrict__ Vb,
-                     float* __restrict__ Qb) {
+                     float* __restrict__ Qb, float* __restrict__ U4) {
   extern __shared__ __align__(16) float pre_smem[];
   float* wqT = pre_smem;                          // [Q][G + 1]
   float* xs = wqT + (size_t)Q * (G + 1);          // [n][K]
@@ -88,9 +88,21 @@ rel_pre_fused_kernel(const float* __restrict__ x, const float* __restrict__ q, c
         v = fmaf(xv.y, wa[j + 1], v);
       }
       U[((size_t)b * n + o) * G + g] = u;
+      if (U4) U4[(((size_t)b * (G / 4) + (g >> 2)) * n + o) * 4 + (g & 3)] = u;
       Vb[((size_t)b * n + o) * G + g] = v;
     }
   }
+}
+
+// U [B, n, G] -> U4 [B][G/4][n][4]
+__global__ void u4_transpose_kernel(const float* __restrict__ U, float* __restrict__ U4, int n, int G4, long long total4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over B * n * G4 float4 groups of U
+  if (i >= total4) return;
+  const int g4 = i % G4;
+  const long long r = i / G4;
+  const int o = r % n;
+  const long long b = r / n;
+  reinterpret_cast<float4*>(U4)[(b * G4 + g4) * n + o] = reinterpret_cast<const float4*>(U)[i];
 }
 
 static size_t rel_pre_fused_smem(const RelShape& s) {
@@ -106,7 +118,7 @@ int relation_pre(const RelShape& s, const float* x, const float* q, const float*
     RN_CUDA(cudaFuncSetAttribute(rel_pre_fused_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rel_pre_fused_kernel<26><<<std::min(s.B, sm_count()), 2 * s.G, smem, st>>>(x, q, g_w[0], fan0, wq, s.fan_in(s.qinj),
                                                                           g_b[s.qinj], g_b[0], s.qinj == 0 ? 1 : 0, s.B,
-                                                                          s.n, s.Q, s.G, pre.U, pre.Vb, pre.Qb);
+                                                                          s.n, s.Q, s.G, pre.U, pre.Vb, pre.Qb, pre.U4);
     RN_LAUNCH_CHECK("rel_pre_fused_kernel");
     return RN_OK;
   }
@@ -126,6 +138,11 @@ int relation_pre(const RelShape& s, const float* x, const float* q, const float*
   else
     add_rowgroup_bias_kernel<<<cdiv(total, 256), 256, 0, st>>>(pre.Vb, g_b[0], total, s.G, 0, 0);
   RN_LAUNCH_CHECK("add_rowgroup_bias_kernel");
+  if (pre.U4) {
+    const long long total4 = (long long)s.B * s.n * (s.G / 4);
+    u4_transpose_kernel<<<cdiv(total4, 256), 256, 0, st>>>(pre.U, pre.U4, s.n, s.G / 4, total4);
+    RN_LAUNCH_CHECK("u4_transpose_kernel");
+  }
   return RN_OK;
 }
 
@@ -474,7 +491,7 @@ extern "C" int rn_relation_workspace(const rn_relation_cfg* cfg, size_t* saved_b
   } else {
     if (!tc_supported(s))
       return fail(RN_ERR_UNSUPPORTED, "tcgen05 path needs G==256, L==4, n*n %% 128 == 0 (G=%d L=%d n=%d)", s.G, s.L, s.n);
-    *saved_bytes = tc_saved_bytes(s, cfg->training != 0);
+    *saved_bytes = tc_saved_bytes(s, cfg->precision, cfg->training != 0);
     *scratch_bytes = tc_scratch_bytes(s, cfg->training != 0);
   }
   return RN_OK;

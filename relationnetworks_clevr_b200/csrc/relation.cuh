@@ -15,11 +15,12 @@ namespace rn {
 
 struct RelShape {
   int B, n, k, Q, G, L, qinj;
+  unsigned flags;
   long long pairs;       // n*n
   long long rows;        // B*n*n
   int fan_in(int l) const { return (l == 0 ? 2 * k : G) + (l == qinj ? Q : 0); }
   explicit RelShape(const rn_relation_cfg& c)
-      : B(c.B), n(c.n), k(c.k), Q(c.Q), G(c.G), L(c.L), qinj(c.qinj), pairs((long long)c.n * c.n),
+      : B(c.B), n(c.n), k(c.k), Q(c.Q), G(c.G), L(c.L), qinj(c.qinj), flags(c.flags), pairs((long long)c.n * c.n),
         rows((long long)c.B * c.n * c.n) {}
 };
 
@@ -29,6 +30,9 @@ struct RelPre {
   float* U;
   float* Vb;
   float* Qb;
+  // optional second copy of U as [B][G/4][n][4] (column groups outermost): a warp whose lanes are consecutive objects
+  // reads one column group of 32 objects as 512 contiguous bytes (the 3-pass forward generates its operand row-per-thread)
+  float* U4 = nullptr;
 };
 
 int relation_pre(const RelShape& s, const float* x, const float* q, const float* const* g_w, const float* const* g_b,
@@ -56,7 +60,7 @@ int simt_relation_bwd(const RelShape& s, const float* dxg, const float* x, const
 
 // tcgen05 path (G == 256, pairs % 128 == 0, L == 4)
 bool tc_supported(const RelShape& s);
-size_t tc_saved_bytes(const RelShape& s, bool training);
+size_t tc_saved_bytes(const RelShape& s, int precision, bool training);
 size_t tc_scratch_bytes(const RelShape& s, bool training);
 int tc_relation_fwd(const RelShape& s, int precision, bool training, const float* x, const float* q,
                     const float* const* g_w, const float* const* g_b, float* xg, void* saved, void* scratch,

@@ -125,6 +125,8 @@ struct ChainParams {
   int skip_dz4_image;              // dgrad: the weight-gradient kernel regenerates dZ4 from the sign bits
   int skip_h1_image;               // training forward: the layer-1 weight-gradient kernel regenerates H1 from U / V'
   int sched;                       // MMA job order (for_each_chain_job)
+  const float* U4;                 // 3-pass forward: U as [B][64 column groups][n][4]
+  int m1_layout0;                  // dgrad: the Z1 sign bits use the same layout as Z2..Z4 (written by the 3-pass forward)
 };
 
 struct Bars {
@@ -747,7 +749,8 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
               bulk_wait_read0();
               mbar_arrive(smem_u32(&bars->a_free[s]));
             }
-            if (p.n == 64) dgrad_mask_tile<2>(taddr, mw, img, swz);
+            if (p.m1_layout0) dgrad_mask_tile<0>(taddr, mw, img, swz);
+            else if (p.n == 64) dgrad_mask_tile<2>(taddr, mw, img, swz);
             else dgrad_mask_tile<1>(taddr, mw, img, swz);
             tc_fence_before_sync();
           } else {
@@ -760,7 +763,7 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
             if (!(p.dbg & 2)) {
               // Z2..Z4 masks: word cc, bit mask_pos(e).  Z1 mask: lane-local layout of generate_h1 (column c -> word
               // (c % 64) / 8, bit (c / 64) * 4 + (c % 8) / 2 + 16 * (c % 2)) or the ballot layout of generate_h1_n64.
-              if (l != 1) dgrad_mask_tile<0>(taddr, mw, a_tile, swz);
+              if (l != 1 || p.m1_layout0) dgrad_mask_tile<0>(taddr, mw, a_tile, swz);
               else if (p.n == 64) dgrad_mask_tile<2>(taddr, mw, a_tile, swz);
               else dgrad_mask_tile<1>(taddr, mw, a_tile, swz);
             }
@@ -788,6 +791,373 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
     if (CTA2) tmem_dealloc2(tmem_base, 512);
     else tmem_dealloc(tmem_base, 512);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// 3-pass training forward (RN_PRECISION_PARITY): fp32-level pre-activations on the tensor cores.
+//
+// Why: with fp16 activations (the 2-pass kernel above) a pre-activation carries ~2^-12 relative error, so ~1e-4 of the
+// ReLU masks differ from an fp32 evaluation; that mask noise, not operand rounding in the backward, is what the
+// gradient error of the round-1 kernels consisted of (2e-3 .. 1e-2 on dq / dW with trained weights, independent of
+// the batch size -- profiles/r02_grad_error_vs_batch.json).  Here every layer computes
+//     Z = A_hi W_hi + A_lo W_hi + A_hi W_lo,   A = A_hi + A_lo, W = W_hi + W_lo  (fp16 splits, fp32 accumulate)
+// which leaves ~2^-21: the masks, and with them the gradients, agree with fp32 to the fp32 conditioning floor.
+//
+// Structure (persistent, one CTA per SM, ONE 128-row tile in flight, 512 threads):
+//   A_hi of the current / next layer: two 64 KB swizzled shared-memory buffers;  A_lo: two 128-column tensor-memory
+//   buffers (packed fp16 pairs, lane = row), read by tcgen05.mma as a TMEM A operand -- it costs no shared-memory
+//   bandwidth and no shared-memory capacity;  accumulators: two N = 128 halves (tensor-memory columns 0..255).
+//   warp 0      weight producer: 32 KB stages = (layer, N-half, K-chunk): [W_hi 128x64 | W_lo 128x64], 3-stage ring
+//   warp 1      MMA issuer: per stage 4 x (SS A_hi W_hi, TS A_lo W_hi) + 4 x SS A_hi W_lo, M128 x N128 x K16
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue of one accumulator half (all 8 warps: 4 lane quarters x 2 column halves of 64): +bias, ReLU,
+//               split into hi (-> shared memory, next layer's A_hi) and lo (-> tcgen05.st, next layer's A_lo), sign bits;
+//               it runs under the MMAs of the other half, and the next layer starts on K-chunks 0,1 as soon as half 0
+//               is written (epi_ready[0]) while half 1 is still in the epilogue.  Last layer: ReLU + pair-sum.
+//   warps 12-15 operand generator: H1 = relu(U[c] + V'[a]) of the NEXT tile, row per thread (U read through its
+//               column-group-major copy U4: 512 contiguous bytes per warp load), under the current tile's last layer.
+// MMA work per tile-layer: 96 x 64 = 6144 cycles; weights: 256 KB per tile-layer as before, i.e. 42 B/cycle -- below
+// the ~54 B/cycle one SM gets out of 32 KB bulk copies (tests/micro/ts_mma_probe.cu), so this kernel is tensor-bound
+// where the 2-pass kernel is copy-bound.
+// ------------------------------------------------------------------------------------------------
+constexpr int k3Threads = 512;
+constexpr int k3WStage = 32768;
+constexpr int k3Stages = 3;
+constexpr int k3SmemW = 2 * kATile;
+constexpr int k3SmemBar = k3SmemW + k3Stages * k3WStage;
+constexpr int k3SmemLaunch = k3SmemBar + 256 + 1024;
+constexpr uint32_t kIdescHalf = idesc_f16(kTileM, 128, 0, 0);
+constexpr uint32_t k3AloCol = 256;            // tensor-memory columns [256, 512): two A_lo buffers of 128 columns
+
+struct Bars3 {
+  uint64_t w_full[k3Stages];
+  uint64_t w_empty[k3Stages];
+  uint64_t gen_ready;       // 128 generator arrivals: the tile's first operand (A_hi + A_lo) is written
+  uint64_t gen_go;          // the buffer of the NEXT tile's first operand is free (MMA commit [+ its image store has been read])
+  uint64_t epi_ready[2];    // 256 epilogue arrivals: K-half kh of the next layer's operand is written
+  uint64_t acc_full[2];     // MMA commit: accumulator half h is complete
+  uint64_t acc_free[2];     // 256 arrivals: the last-layer epilogue has drained accumulator half h
+  uint32_t tmem_base;
+};
+
+// image index (((layer * 2 + half) * 4 + kc) * 2 + pass) * 16 KB: 128 N rows x 64 K, SWIZZLE_128B
+__global__ void pack_weights3_kernel(PackArgs args, __half* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= kTcLayers * kG * (kG / 8)) return;
+  const int layer = idx / (kG * (kG / 8));
+  const int rem = idx % (kG * (kG / 8));
+  const int nrow = rem / (kG / 8);
+  const int kg = rem % (kG / 8);
+  const float* w = args.w[layer] + (size_t)nrow * args.ld[layer] + kg * 8;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float v0 = w[2 * e], v1 = w[2 * e + 1];
+    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+    __half2 hh = __halves2half2(h0, h1);
+    __half2 ll = __floats2half2_rn(v0 - __half2float(h0), v1 - __half2float(h1));
+    hi[e] = *reinterpret_cast<uint32_t*>(&hh);
+    lo[e] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  char* base = reinterpret_cast<char*>(out) + ((size_t)((layer * 2 + (nrow >> 7)) * kNKC + kg / 8) * 2) * 16384 +
+               sw128_offset(nrow & 127, (kg % 8) * 8);
+  *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(base + 16384) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// relu(z) as an fp16 pair (hi) and the fp16 pair of what the rounding dropped (lo)
+__device__ __forceinline__ void split_relu_half2(float z0, float z1, uint32_t& hi, uint32_t& lo) {
+  const float r0 = fmaxf(z0, 0.f), r1 = fmaxf(z1, 0.f);
+  const __half2 h = __floats2half2_rn(r0, r1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <bool SAVE>
+__global__ void __launch_bounds__(k3Threads, 1) rn_g_fwd3_kernel(const ChainParams p) {
+  extern __shared__ char smem_raw[];
+  char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  Bars3* bars = reinterpret_cast<Bars3*>(smem + k3SmemBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = tiles_of_cta(p.num_tiles);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < k3Stages; ++s) {
+      mbar_init(smem_u32(&bars->w_full[s]), 1);
+      mbar_init(smem_u32(&bars->w_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bars->gen_ready), 128);
+    mbar_init(smem_u32(&bars->gen_go), SAVE ? 2 : 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(smem_u32(&bars->epi_ready[h]), 256);
+      mbar_init(smem_u32(&bars->acc_full[h]), 1);
+      mbar_init(smem_u32(&bars->acc_free[h]), 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= weight producer =================
+      uint32_t stage = 0, phase = 0;
+      for (int i = 0; i < my_tiles; ++i)
+        for (int job = 0; job < kTcLayers * 2 * kNKC; ++job) {          // (layer, half, kc) in image order
+          mbar_wait(smem_u32(&bars->w_empty[stage]), phase ^ 1);
+          const uint32_t full = smem_u32(&bars->w_full[stage]);
+          mbar_expect_tx(full, k3WStage);
+          bulk_g2s(smem_u32(smem + k3SmemW + stage * k3WStage), reinterpret_cast<const char*>(p.wpack) + (size_t)job * k3WStage,
+                   k3WStage, full);
+          if (++stage == k3Stages) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      uint32_t stage = 0, phase = 0, gen_phase = 0;
+      uint32_t epi_phase[2] = {0, 0}, free_phase[2] = {0, 0};
+      uint32_t j = 0;                                  // operand counter: operand j lives in buffer j & 1
+      for (int i = 0; i < my_tiles; ++i)
+        for (int layer = 0; layer < kTcLayers; ++layer, ++j) {
+          const uint32_t a_base = smem_u32(smem + (j & 1) * kATile);
+          const uint32_t alo = tmem_base + k3AloCol + (j & 1) * 128;
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t d_tmem = tmem_base + h * 128;
+            if (layer == 0) {
+              if (h == 0) {
+                mbar_wait(smem_u32(&bars->gen_ready), gen_phase);
+                gen_phase ^= 1;
+              }
+              if (i > 0) {                              // the previous tile's pair-sum epilogue has drained this half
+                mbar_wait(smem_u32(&bars->acc_free[h]), free_phase[h]);
+                free_phase[h] ^= 1;
+              }
+            }
+            uint32_t accumulate = 0;
+            for (int kc = 0; kc < kNKC; ++kc) {
+              if (layer > 0 && h == 0 && (kc & 1) == 0) {      // K-half kc / 2 of this layer's operand is written
+                mbar_wait(smem_u32(&bars->epi_ready[kc >> 1]), epi_phase[kc >> 1]);
+                epi_phase[kc >> 1] ^= 1;
+              }
+              mbar_wait(smem_u32(&bars->w_full[stage]), phase);
+              tc_fence_after_sync();
+              const uint32_t b_base = smem_u32(smem + k3SmemW + stage * k3WStage);
+#pragma unroll
+              for (int k = 0; k < kKC / 16; ++k) {
+                const uint64_t ad = smem_desc_sw128(a_base + kc * kAChunk + k * 32, 16, 1024);
+                const uint64_t bd = smem_desc_sw128(b_base + k * 32, 16, 1024);
+                mma_f16_ss(d_tmem, ad, bd, kIdescHalf, accumulate);
+                accumulate = 1;
+                mma_f16_ts(d_tmem, alo + kc * 32 + k * 8, bd, kIdescHalf, 1);
+              }
+#pragma unroll
+              for (int k = 0; k < kKC / 16; ++k) {
+                const uint64_t ad = smem_desc_sw128(a_base + kc * kAChunk + k * 32, 16, 1024);
+                const uint64_t bd = smem_desc_sw128(b_base + 16384 + k * 32, 16, 1024);
+                mma_f16_ss(d_tmem, ad, bd, kIdescHalf, 1);
+              }
+              mma_commit(smem_u32(&bars->w_empty[stage]));
+              if (++stage == k3Stages) { stage = 0; phase ^= 1; }
+            }
+            mma_commit(smem_u32(&bars->acc_full[h]));
+            // the second layer's operand buffer is where the generator writes the next tile's first operand
+            if (layer == 1 && h == 1) mma_commit(smem_u32(&bars->gen_go));
+          }
+        }
+    }
+  } else if (warp >= 12) {
+    // ================= operand generator =================
+    const int q = warp & 3, gt = threadIdx.x - 384;
+    const int row = q * 32 + lane;
+    uint32_t swz[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) swz[k] = sw128_offset(row, k * 8);
+    uint32_t go_phase = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int b = tile / p.tiles_per_sample;
+      const int pr = (tile % p.tiles_per_sample) * kTileM + row;
+      const int a = pr / p.n, c = pr - a * p.n;
+      const uint32_t buf = (3u * (uint32_t)i) & 1u;
+      if (i > 0) {
+        mbar_wait(smem_u32(&bars->gen_go), go_phase);
+        go_phase ^= 1;
+        tc_fence_after_sync();
+      }
+      const float4* up = reinterpret_cast<const float4*>(p.U4) + (size_t)b * (kG / 4) * p.n + c;      // + g4 * n
+      const float4* vp = reinterpret_cast<const float4*>(p.Vb + ((size_t)b * p.n + a) * kG);
+      char* a_dst = smem + buf * kATile;
+      const uint32_t alo = tmem_base + ((uint32_t)(q * 32) << 16) + k3AloCol + buf * 128;
+      uint32_t mw[8];
+#pragma unroll 1
+      for (int c64 = 0; c64 < 4; ++c64) {                 // 64 columns = 32 tensor-memory columns per store
+        uint32_t lo[32];
+#pragma unroll
+        for (int c32 = 0; c32 < 2; ++c32) {
+          const int cc = c64 * 2 + c32;
+          float4 u[8], v[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            u[g] = __ldg(up + (size_t)(cc * 8 + g) * p.n);
+            v[g] = __ldg(vp + cc * 8 + g);
+          }
+          uint32_t bits = 0;
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const float4 u0 = u[2 * g8], u1 = u[2 * g8 + 1], v0 = v[2 * g8], v1 = v[2 * g8 + 1];
+            uint4 o;
+            uint32_t* l4 = lo + c32 * 16 + g8 * 4;
+            split_relu_half2(u0.x + v0.x, u0.y + v0.y, o.x, l4[0]);
+            split_relu_half2(u0.z + v0.z, u0.w + v0.w, o.y, l4[1]);
+            split_relu_half2(u1.x + v1.x, u1.y + v1.y, o.z, l4[2]);
+            split_relu_half2(u1.z + v1.z, u1.w + v1.w, o.w, l4[3]);
+            if (SAVE) {
+              bits |= half2_pos_mask(o.x) & mask_pair_const(g8 * 4 + 0);
+              bits |= half2_pos_mask(o.y) & mask_pair_const(g8 * 4 + 1);
+              bits |= half2_pos_mask(o.z) & mask_pair_const(g8 * 4 + 2);
+              bits |= half2_pos_mask(o.w) & mask_pair_const(g8 * 4 + 3);
+            }
+            const int col = cc * 32 + g8 * 8;
+            *reinterpret_cast<uint4*>(a_dst + (col >> 6) * kAChunk + swz[(col >> 3) & 7]) = o;
+          }
+          mw[cc] = bits;
+        }
+        tmem_st32(alo + c64 * 32, lo);
+      }
+      tmem_st_wait();
+      if (SAVE) {
+        uint32_t* mrow = p.masks + ((size_t)tile * kTileM + row) * 8;       // masks[0] = M1, same layout as M2..M4
+        *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+      }
+      fence_proxy_async_smem();
+      if (SAVE && !p.skip_h1_image) {
+        named_bar_sync(3, 128);
+        if (gt == 0) {
+          bulk_s2g(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile, smem_u32(a_dst), kATile);
+          bulk_commit();
+          bulk_wait_read0();
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(smem_u32(&bars->gen_ready));
+    }
+    if (SAVE && gt == 0) bulk_wait0();
+  } else if (warp >= 4) {
+    // ================= epilogue warps =================
+    const int q = warp & 3, ch = (warp - 4) >> 2, et = threadIdx.x - 128;
+    const int row = q * 32 + lane;
+    uint32_t swz[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) swz[k] = sw128_offset(row, k * 8);
+    uint32_t acc_phase[2] = {0, 0};
+    uint32_t j = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int b = tile / p.tiles_per_sample;
+      for (int layer = 0; layer < kTcLayers; ++layer, ++j) {
+        const uint32_t nbuf = (j + 1) & 1;
+        const float* bias = p.bias[layer] + (size_t)b * p.bias_stride[layer];
+        for (int h = 0; h < 2; ++h) {
+          const int colbase = h * 128 + ch * 64;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + colbase;
+          uint32_t* mrow = SAVE ? p.masks + (((size_t)(layer + 1) * p.num_tiles + tile) * kTileM + row) * 8 + (colbase >> 5) : nullptr;
+          mbar_wait(smem_u32(&bars->acc_full[h]), acc_phase[h]);
+          acc_phase[h] ^= 1;
+          tc_fence_after_sync();
+          if (layer < kTcLayers - 1) {
+            // thread 128 has finished waiting for the image store that read this buffer two operands ago
+            if (SAVE && h == 0) named_bar_sync(1, 256);
+            char* a_dst = smem + nbuf * kATile;
+            uint32_t lo[32], mw[2];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t r[32];
+              tmem_ld32(taddr + cc * 32, r);
+              tmem_ld_wait();
+              uint32_t bits = 0;
+#pragma unroll
+              for (int g4 = 0; g4 < 4; ++g4) {
+                const int col = colbase + cc * 32 + g4 * 8;
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+                uint4 o;
+                uint32_t* l4 = lo + cc * 16 + g4 * 4;
+                split_relu_half2(__uint_as_float(r[g4 * 8 + 0]) + b0.x, __uint_as_float(r[g4 * 8 + 1]) + b0.y, o.x, l4[0]);
+                split_relu_half2(__uint_as_float(r[g4 * 8 + 2]) + b0.z, __uint_as_float(r[g4 * 8 + 3]) + b0.w, o.y, l4[1]);
+                split_relu_half2(__uint_as_float(r[g4 * 8 + 4]) + b1.x, __uint_as_float(r[g4 * 8 + 5]) + b1.y, o.z, l4[2]);
+                split_relu_half2(__uint_as_float(r[g4 * 8 + 6]) + b1.z, __uint_as_float(r[g4 * 8 + 7]) + b1.w, o.w, l4[3]);
+                if (SAVE) {
+                  bits |= half2_pos_mask(o.x) & mask_pair_const(g4 * 4 + 0);
+                  bits |= half2_pos_mask(o.y) & mask_pair_const(g4 * 4 + 1);
+                  bits |= half2_pos_mask(o.z) & mask_pair_const(g4 * 4 + 2);
+                  bits |= half2_pos_mask(o.w) & mask_pair_const(g4 * 4 + 3);
+                }
+                *reinterpret_cast<uint4*>(a_dst + (col >> 6) * kAChunk + swz[(col >> 3) & 7]) = o;
+              }
+              mw[cc] = bits;
+            }
+            tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + k3AloCol + nbuf * 128 + (colbase >> 1), lo);
+            tmem_st_wait();
+            if (SAVE) *reinterpret_cast<uint2*>(mrow) = make_uint2(mw[0], mw[1]);
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            mbar_arrive(smem_u32(&bars->epi_ready[h]));
+            if (SAVE && h == 1) {
+              named_bar_sync(2, 256);                   // both halves written and fenced by every epilogue thread
+              if (et == 0) {
+                bulk_s2g(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + layer + 1) * kATile, smem_u32(a_dst), kATile);
+                bulk_commit();
+                bulk_wait_read0();
+                if (layer == 0) mbar_arrive(smem_u32(&bars->gen_go));
+              }
+            }
+          } else {
+            // last layer: ReLU + pair-sum (column sums over this warp's 32 rows)
+            float* part = p.xg_part + ((size_t)tile * 4 + q) * kG;
+            uint32_t mw[2];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t r[32];
+              tmem_ld32(taddr + cc * 32, r);
+              tmem_ld_wait();
+              float x[32];
+              uint32_t bits = 0;
+#pragma unroll
+              for (int e4 = 0; e4 < 8; ++e4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + colbase + cc * 32 + e4 * 4));
+                x[e4 * 4 + 0] = fmaxf(__uint_as_float(r[e4 * 4 + 0]) + bv.x, 0.f);
+                x[e4 * 4 + 1] = fmaxf(__uint_as_float(r[e4 * 4 + 1]) + bv.y, 0.f);
+                x[e4 * 4 + 2] = fmaxf(__uint_as_float(r[e4 * 4 + 2]) + bv.z, 0.f);
+                x[e4 * 4 + 3] = fmaxf(__uint_as_float(r[e4 * 4 + 3]) + bv.w, 0.f);
+              }
+              if (SAVE) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) bits |= half2_pos_mask(pack_half2(x[2 * e], x[2 * e + 1])) & mask_pair_const(e);
+              }
+              mw[cc] = bits;
+              part[colbase + cc * 32 + lane] = warp_transpose_sum(x, lane);
+            }
+            if (SAVE) *reinterpret_cast<uint2*>(mrow) = make_uint2(mw[0], mw[1]);
+            tc_fence_before_sync();
+            mbar_arrive(smem_u32(&bars->acc_free[h]));
+          }
+        }
+      }
+    }
+    if (SAVE && et == 0) bulk_wait0();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1263,10 +1633,16 @@ struct TcSaved {
   uint32_t* masks;     // [4][tiles][128][8]
 };
 
-static TcSaved tc_carve_saved(const RelShape& s, void* saved, bool training) {
+// the training forward of the parity mode is the 3-pass kernel unless the caller asks for the 2-pass one
+static bool tc_fwd3(const RelShape& s, int precision, bool training) {
+  return training && precision == RN_PRECISION_PARITY && !(s.flags & RN_REL_FLAG_FWD_2PASS);
+}
+
+static TcSaved tc_carve_saved(const RelShape& s, void* saved, bool training, bool fwd3) {
   Carver c(saved);
   TcSaved o;
   o.pre.U = c.take<float>((size_t)s.B * s.n * s.G);
+  if (fwd3) o.pre.U4 = c.take<float>((size_t)s.B * s.n * s.G);
   o.pre.Vb = c.take<float>((size_t)s.B * s.n * s.G);
   o.pre.Qb = c.take<float>((size_t)s.B * s.G);
   o.wpack = reinterpret_cast<__half*>(c.take<char>(wpack_bytes()));
@@ -1276,9 +1652,10 @@ static TcSaved tc_carve_saved(const RelShape& s, void* saved, bool training) {
   return o;
 }
 
-size_t tc_saved_bytes(const RelShape& s, bool training) {
+size_t tc_saved_bytes(const RelShape& s, int precision, bool training) {
   const size_t tiles = s.rows / kTileM;
   size_t b = 2 * round_up((size_t)s.B * s.n * s.G * 4, 256) + round_up((size_t)s.B * s.G * 4, 256) + round_up(wpack_bytes(), 256);
+  if (tc_fwd3(s, precision, training)) b += round_up((size_t)s.B * s.n * s.G * 4, 256);
   if (training) b += round_up(tiles * 3 * kATile, 256) + round_up(tiles * 4 * kTileM * 8 * 4, 256);
   return b;
 }
@@ -1394,11 +1771,13 @@ static int launch_chain(const ChainParams& p, cudaStream_t st) {
 int tc_relation_fwd(const RelShape& s, int precision, bool training, const float* x, const float* q,
                     const float* const* g_w, const float* const* g_b, float* xg, void* saved, void* scratch,
                     cudaStream_t st) {
-  TcSaved sv = tc_carve_saved(s, saved, training);
+  const bool fwd3 = tc_fwd3(s, precision, training);
+  TcSaved sv = tc_carve_saved(s, saved, training, fwd3);
   RN_TRY(relation_pre(s, x, q, g_w, g_b, sv.pre, st));
   PackArgs pa;
   fill_pack_args(s, g_w, pa);
-  pack_weights_kernel<<<cdiv(kTcLayers * kG * (kG / 8), 256), 256, 0, st>>>(pa, sv.wpack, 0);
+  if (fwd3) pack_weights3_kernel<<<cdiv(kTcLayers * kG * (kG / 8), 256), 256, 0, st>>>(pa, sv.wpack);
+  else pack_weights_kernel<<<cdiv(kTcLayers * kG * (kG / 8), 256), 256, 0, st>>>(pa, sv.wpack, 0);
   RN_LAUNCH_CHECK("pack_weights_kernel");
 
   ChainParams p = {};
@@ -1424,8 +1803,16 @@ int tc_relation_fwd(const RelShape& s, int precision, bool training, const float
   p.tiles_per_sample = (int)(s.pairs / kTileM);
   p.num_tiles = (int)(s.rows / kTileM);
   p.passes = precision == RN_PRECISION_FAST ? 1 : 2;
-  if (training) RN_TRY(launch_chain<kFwdTrain>(p, st));
-  else RN_TRY(launch_chain<kFwdEval>(p, st));
+  p.U4 = sv.pre.U4;
+  if (fwd3) {
+    RN_CUDA(cudaFuncSetAttribute(rn_g_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemLaunch));
+    rn_g_fwd3_kernel<true><<<std::min(p.num_tiles, sm_count()), k3Threads, k3SmemLaunch, st>>>(p);
+    RN_LAUNCH_CHECK("rn_g_fwd3_kernel");
+  } else if (training) {
+    RN_TRY(launch_chain<kFwdTrain>(p, st));
+  } else {
+    RN_TRY(launch_chain<kFwdEval>(p, st));
+  }
   // x_g[b] = sum over the sample's tiles and the 4 row quarters (fixed order -> deterministic)
   RN_TRY(colsum(p.xg_part, xg, s.G, s.B, 1, (long long)p.tiles_per_sample * 4, 0, 1, p.tiles_per_sample * 4, st));
   return RN_OK;
@@ -1434,7 +1821,8 @@ int tc_relation_fwd(const RelShape& s, int precision, bool training, const float
 int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const float* x, const float* q,
                     const float* const* g_w, const void* saved, float* dx, float* dq, float* const* dg_w,
                     float* const* dg_b, void* scratch, cudaStream_t st) {
-  TcSaved sv = tc_carve_saved(s, const_cast<void*>(saved), true);
+  const bool fwd3 = tc_fwd3(s, precision, true);
+  TcSaved sv = tc_carve_saved(s, const_cast<void*>(saved), true, fwd3);
   TcBwdScratch ws = tc_carve_bwd(s, scratch);
   const int tps = (int)(s.pairs / kTileM);
   const int tiles = (int)(s.rows / kTileM);
@@ -1459,10 +1847,10 @@ int tc_relation_bwd(const RelShape& s, int precision, const float* dxg, const fl
   p.n = s.n;
   p.tiles_per_sample = tps;
   p.num_tiles = tiles;
-  // one pass (W_hi only) for the data gradient unless RN_B200_DGRAD_PASSES=2: fp16 weight rounding (2^-12 relative,
-  // independent per weight) is far below the ReLU-mask noise of the fp16-activation network
-  static const int dgrad_passes = []() { const char* e = getenv("RN_B200_DGRAD_PASSES"); return (e && e[0] == '2') ? 2 : 1; }();
-  p.passes = precision == RN_PRECISION_FAST ? 1 : dgrad_passes;
+  // one pass (W_hi only) for the data gradient unless RN_REL_FLAG_DGRAD_2PASS: fp16 weight rounding (2^-12 relative,
+  // independent per weight) does not move the gradient error (measured: profiles/r02_grad_error_vs_batch.json)
+  p.passes = (precision != RN_PRECISION_FAST && (s.flags & RN_REL_FLAG_DGRAD_2PASS)) ? 2 : 1;
+  p.m1_layout0 = fwd3 ? 1 : 0;
   p.masks = sv.masks;
   p.dxg = dxg;
   p.scale = ws.scale;

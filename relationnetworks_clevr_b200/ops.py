@@ -6,6 +6,7 @@ these ops happens in librn_b200.so.  Every op requires CUDA tensors and raises o
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Tuple
 
 import torch
@@ -100,8 +101,15 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
-def relation_cfg(B, n, k, Q, G, L, qinj, precision: str, training: bool) -> RelationCfg:
-    return RelationCfg(B, n, k, Q, G, L, qinj, PRECISION[precision], int(training))
+# rn_relation_cfg.flags (include/rn_b200.h RN_REL_FLAG_*); diagnostics may set RN_B200_REL_FLAGS
+REL_FLAG_FWD_2PASS = 1
+REL_FLAG_DGRAD_2PASS = 2
+relation_flags = int(os.environ.get("RN_B200_REL_FLAGS", "0"))
+
+
+def relation_cfg(B, n, k, Q, G, L, qinj, precision: str, training: bool, flags=None) -> RelationCfg:
+    return RelationCfg(B, n, k, Q, G, L, qinj, PRECISION[precision], int(training),
+                       relation_flags if flags is None else flags)
 
 
 def tc_supported(n: int, G: int, L: int, k: int = 26, Q: int = 128, qinj: int = 0) -> bool:
