@@ -362,7 +362,7 @@ __device__ __forceinline__ void dgrad_mask_tile(uint32_t taddr, const uint32_t (
 // and half the shared-memory operand reads per SM -- the 1-CTA form is shared-memory-bandwidth bound.
 __device__ long long g_chain_prof[160][16];
 #define PROF_T0() long long _t0 = 0; if (prof) _t0 = clock64();
-#define PROF_ACC(i) if (prof) { const long long _t1 = clock64(); pacc[i] += _t1 - _t0; _t0 = _t1; }
+#define PROF_ACC(i) if (prof) { const long long _t1 = clock64(); pacc[(i) < (int)(sizeof(pacc) / sizeof(pacc[0])) ? (i) : 0] += _t1 - _t0; _t0 = _t1; }
 
 // Static MMA job order shared by the weight producer and the MMA issuer (the epilogue warps are driven by barriers only).
 // sched 0: round r = [s0 L1, s1 L1, s0 L2, s1 L2, s0 L3, s1 L3]  (strict alternation)
@@ -467,12 +467,16 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
       });
     }
   } else if (warp == 1) {
-    if (lane == 0 && (!CTA2 || rank == 0)) {
+    if (!CTA2 || rank == 0) {
       // ================= MMA issuer (pair mode: leader CTA only) =================
+      // The whole warp runs the loop (warp-uniform control flow, descriptors stepped with one 32-bit add in uniform
+      // registers); only the tcgen05 instructions are predicated on one elected lane -- see rn_g_fwd3_kernel.
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
       const bool prof = (p.dbg & 8) != 0;
       long long pacc[4] = {0, 0, 0, 0};
+      constexpr uint32_t kDescHi = smem_desc_hi_sw128(1024);
+      const bool leader = elect_one();
       PROF_T0();
       for_each_chain_job(my_tiles, CTA2 ? 0 : p.sched, [&](int s, int) {
             if (CTA2) mbar_wait_cluster(smem_u32(&bars->a_full[s]), a_phase[s]);
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
             PROF_ACC(0);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + s * kG;
-            const uint32_t a_base = smem_u32(smem + kSmemA + s * kATile);
+            const uint32_t a_lo = smem_desc_lo_sw128(smem_u32(smem + kSmemA + s * kATile), 16);
             uint32_t accumulate = 0;
             const int reps = (p.dbg & 1) ? p.passes : 1;
             for (int pass = 0; pass < ((p.dbg & 1) ? 1 : p.passes); ++pass)
@@ -490,27 +494,33 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
                 if (CTA2) mbar_wait_cluster(smem_u32(&bars->peer_full[stage]), phase);
                 PROF_ACC(1);
                 tc_fence_after_sync();
-                const uint32_t b_base = smem_u32(smem + kSmemW + stage * STAGE_BYTES);
-                for (int rep = 0; rep < reps; ++rep)
+                const uint32_t b_lo = smem_desc_lo_sw128(smem_u32(smem + kSmemW + stage * STAGE_BYTES), 16);
+                const uint32_t a_kc = a_lo + kc * (kAChunk >> 4);
+                if (leader) {
+                  for (int rep = 0; rep < reps; ++rep)
 #pragma unroll
-                for (int k = 0; k < kKC / 16; ++k) {
-                  const uint64_t ad = smem_desc_sw128(a_base + kc * kAChunk + k * 32, 16, 1024);
-                  const uint64_t bd = smem_desc_sw128(b_base + k * 32, 16, 1024);
-                  if (CTA2) mma_f16_ss_2cta(d_tmem, ad, bd, kIdescFwd2, accumulate);
-                  else mma_f16_ss(d_tmem, ad, bd, kIdescFwd, accumulate);
-                  accumulate = 1;
+                  for (int k = 0; k < kKC / 16; ++k) {
+                    const uint64_t ad = desc_pack(a_kc + 2 * k, kDescHi);
+                    const uint64_t bd = desc_pack(b_lo + 2 * k, kDescHi);
+                    if (CTA2) mma_f16_ss_2cta(d_tmem, ad, bd, kIdescFwd2, accumulate | (uint32_t)(k > 0 || rep > 0));
+                    else mma_f16_ss(d_tmem, ad, bd, kIdescFwd, accumulate | (uint32_t)(k > 0 || rep > 0));
+                  }
+                  // ring stage free (in both CTAs) once these MMAs retire
+                  if (CTA2) mma_commit_2cta(smem_u32(&bars->w_empty[stage]), 3);
+                  else if (!(p.dbg & 4)) mma_commit(smem_u32(&bars->w_empty[stage]));
                 }
-                // ring stage free (in both CTAs) once these MMAs retire
-                if (CTA2) mma_commit_2cta(smem_u32(&bars->w_empty[stage]), 3);
-                else if (!(p.dbg & 4)) mma_commit(smem_u32(&bars->w_empty[stage]));
+                accumulate = 1;
                 if (!(p.dbg & 4) && ++stage == NST) { stage = 0; phase ^= 1; }
               }
             // accumulator of (slot, layer) complete (in both CTAs)
-            if (CTA2) mma_commit_2cta(smem_u32(&bars->acc_full[s]), 3);
-            else mma_commit(smem_u32(&bars->acc_full[s]));
+            if (leader) {
+              if (CTA2) mma_commit_2cta(smem_u32(&bars->acc_full[s]), 3);
+              else mma_commit(smem_u32(&bars->acc_full[s]));
+            }
+            __syncwarp();
             PROF_ACC(2);
       });
-      if (prof) for (int i = 0; i < 3; ++i) g_chain_prof[blockIdx.x][8 + i] = pacc[i];
+      if (prof && lane == 0) for (int i = 0; i < 3; ++i) g_chain_prof[blockIdx.x][8 + i] = pacc[i];
     } else if (CTA2 && lane == 0) {
       // ================= peer CTA relay: tell the leader when this CTA's half of each chunk has landed =================
       uint32_t stage = 0, phase = 0;
@@ -821,8 +831,10 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kFwdThreads, 1) rn_g_chain
 // the ~54 B/cycle one SM gets out of 32 KB bulk copies (tests/micro/ts_mma_probe.cu), so this kernel is tensor-bound
 // where the 2-pass kernel is copy-bound.
 // ------------------------------------------------------------------------------------------------
-constexpr int k3Threads = 512;
-constexpr int k3WStage = 32768;
+constexpr int k3Threads = 640;            // 4 control warps, 8 epilogue warps, 8 generator warps
+constexpr int k3WSub = 16384;              // one weight sub-chunk: (layer, N-half, K-chunk, hi | lo) = 128 N rows x 64 K
+constexpr int k3SubPerStage = 2;
+constexpr int k3WStage = k3SubPerStage * k3WSub;      // 32 KB per bulk copy, 3 in the ring (2 x 48 KB measured slower: prefetch depth)
 constexpr int k3Stages = 3;
 constexpr int k3SmemW = 2 * kATile;
 constexpr int k3SmemBar = k3SmemW + k3Stages * k3WStage;
@@ -833,11 +845,13 @@ constexpr uint32_t k3AloCol = 256;            // tensor-memory columns [256, 512
 struct Bars3 {
   uint64_t w_full[k3Stages];
   uint64_t w_empty[k3Stages];
-  uint64_t gen_ready;       // 128 generator arrivals: the tile's first operand (A_hi + A_lo) is written
+  uint64_t gen_ready;       // 256 generator arrivals: the tile's first operand (A_hi + A_lo) is written
   uint64_t gen_go;          // the buffer of the NEXT tile's first operand is free (MMA commit [+ its image store has been read])
   uint64_t epi_ready[2];    // 256 epilogue arrivals: K-half kh of the next layer's operand is written
   uint64_t acc_full[2];     // MMA commit: accumulator half h is complete
   uint64_t acc_free[2];     // 256 arrivals: the last-layer epilogue has drained accumulator half h
+  uint64_t img_ready;       // 256 epilogue arrivals: a complete operand (H2 / H3) sits in shared memory, ready for its image store
+  uint64_t h3_done;         // the H3 image store has finished reading its buffer (the next tile's H2 overwrites it)
   uint32_t tmem_base;
 };
 
@@ -876,7 +890,9 @@ __device__ __forceinline__ void split_relu_half2(float z0, float z1, uint32_t& h
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <bool SAVE>
+#define PROF3_T0() uint32_t _t0 = 0; if (prof) _t0 = (uint32_t)clock();
+#define PROF3_ACC(i) if (prof) { const uint32_t _t1 = (uint32_t)clock(); pacc[(i) < (int)(sizeof(pacc) / sizeof(pacc[0])) ? (i) : 0] += _t1 - _t0; _t0 = _t1; }
+template <bool SAVE, bool PROF>
 __global__ void __launch_bounds__(k3Threads, 1) rn_g_fwd3_kernel(const ChainParams p) {
   extern __shared__ char smem_raw[];
   char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -889,7 +905,9 @@ __global__ void __launch_bounds__(k3Threads, 1) rn_g_fwd3_kernel(const ChainPara
       mbar_init(smem_u32(&bars->w_full[s]), 1);
       mbar_init(smem_u32(&bars->w_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bars->gen_ready), 128);
+    mbar_init(smem_u32(&bars->gen_ready), 256);
+    mbar_init(smem_u32(&bars->img_ready), 256);
+    mbar_init(smem_u32(&bars->h3_done), 1);
     mbar_init(smem_u32(&bars->gen_go), SAVE ? 2 : 1);
     for (int h = 0; h < 2; ++h) {
       mbar_init(smem_u32(&bars->epi_ready[h]), 256);
@@ -904,142 +922,211 @@ __global__ void __launch_bounds__(k3Threads, 1) rn_g_fwd3_kernel(const ChainPara
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0) {
+  if (warp < 4) {
+  reg_dec<48>();          // (the register budgets of the three roles must not share code after a join: ptxas assumes the minimum)
+  if (warp == 3) {
+    if (SAVE && lane == 0) {
+      // ================= image storer: streams H2 / H3 (the A_hi operands) to HBM for the weight-gradient kernel =================
+      uint32_t ph = 0, j = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        for (int layer = 0; layer < kTcLayers; ++layer, ++j) {
+          if (layer == kTcLayers - 1) continue;
+          mbar_wait(smem_u32(&bars->img_ready), ph);
+          ph ^= 1;
+          if (!(p.dbg & 64))      // (timing ablation: no image stores)
+            bulk_s2g(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + layer + 1) * kATile, smem_u32(smem + ((j + 1) & 1) * kATile), kATile);
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive(smem_u32(layer == 0 ? &bars->gen_go : &bars->h3_done));
+        }
+      }
+      bulk_wait0();
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       // ================= weight producer =================
+      // the weight image is a stream of 48 sub-chunks per tile in consumption order (layer, half, kc, hi | lo); one copy = k3SubPerStage of them
       uint32_t stage = 0, phase = 0;
       for (int i = 0; i < my_tiles; ++i)
-        for (int job = 0; job < kTcLayers * 2 * kNKC; ++job) {          // (layer, half, kc) in image order
+        for (int v = 0; v < kTcLayers * 2 * kNKC * 2 / k3SubPerStage; ++v) {
           mbar_wait(smem_u32(&bars->w_empty[stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars->w_full[stage]);
           mbar_expect_tx(full, k3WStage);
-          bulk_g2s(smem_u32(smem + k3SmemW + stage * k3WStage), reinterpret_cast<const char*>(p.wpack) + (size_t)job * k3WStage,
+          bulk_g2s(smem_u32(smem + k3SmemW + stage * k3WStage), reinterpret_cast<const char*>(p.wpack) + (size_t)v * k3WStage,
                    k3WStage, full);
           if (++stage == k3Stages) { stage = 0; phase ^= 1; }
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ================= MMA issuer =================
-      uint32_t stage = 0, phase = 0, gen_phase = 0;
-      uint32_t epi_phase[2] = {0, 0}, free_phase[2] = {0, 0};
+      // The WHOLE warp runs this loop (warp-uniform control flow, descriptors in uniform registers); only the tcgen05
+      // instructions are predicated on one elected lane.  A lane-0-only branch makes the compiler wrap every MMA in a
+      // divergence loop and pass the descriptors through vector registers: measured, that instruction stream -- not the
+      // tensor pipe, not the weight copies -- set the pace of the kernel.
+      uint32_t stage = 0, phase = 0, gen_phase = 0, sub = 0;      // sub: sub-chunk within the current 48 KB stage
+      uint32_t epi_phase = 0, free_phase = 0;      // bit h = phase of barrier [h] (no dynamically indexed arrays)
       uint32_t j = 0;                                  // operand counter: operand j lives in buffer j & 1
+      constexpr bool prof = PROF;
+      uint32_t pacc[PROF ? 8 : 1] = {0};
+      const uint32_t t_begin = PROF ? (uint32_t)clock() : 0u;
+      constexpr uint32_t kDescHi = smem_desc_hi_sw128(1024);
+      const bool leader = elect_one();
+      PROF3_T0();
       for (int i = 0; i < my_tiles; ++i)
         for (int layer = 0; layer < kTcLayers; ++layer, ++j) {
-          const uint32_t a_base = smem_u32(smem + (j & 1) * kATile);
+          const uint32_t a_lo = smem_desc_lo_sw128(smem_u32(smem + (j & 1) * kATile), 16);
           const uint32_t alo = tmem_base + k3AloCol + (j & 1) * 128;
           for (int h = 0; h < 2; ++h) {
             const uint32_t d_tmem = tmem_base + h * 128;
             if (layer == 0) {
               if (h == 0) {
+                PROF3_ACC(5);
                 mbar_wait(smem_u32(&bars->gen_ready), gen_phase);
                 gen_phase ^= 1;
+                PROF3_ACC(0);
               }
               if (i > 0) {                              // the previous tile's pair-sum epilogue has drained this half
-                mbar_wait(smem_u32(&bars->acc_free[h]), free_phase[h]);
-                free_phase[h] ^= 1;
+                PROF3_ACC(5);
+                mbar_wait(smem_u32(&bars->acc_free[h]), (free_phase >> h) & 1u);
+                free_phase ^= 1u << h;
+                PROF3_ACC(1);
               }
             }
             uint32_t accumulate = 0;
+#pragma unroll 1
             for (int kc = 0; kc < kNKC; ++kc) {
               if (layer > 0 && h == 0 && (kc & 1) == 0) {      // K-half kc / 2 of this layer's operand is written
-                mbar_wait(smem_u32(&bars->epi_ready[kc >> 1]), epi_phase[kc >> 1]);
-                epi_phase[kc >> 1] ^= 1;
+                PROF3_ACC(5);
+                mbar_wait(smem_u32(&bars->epi_ready[kc >> 1]), (epi_phase >> (kc >> 1)) & 1u);
+                epi_phase ^= 1u << (kc >> 1);
+                PROF3_ACC(2 + (kc >> 1));
               }
-              mbar_wait(smem_u32(&bars->w_full[stage]), phase);
-              tc_fence_after_sync();
-              const uint32_t b_base = smem_u32(smem + k3SmemW + stage * k3WStage);
+              const uint32_t a_kc = a_lo + kc * (kAChunk >> 4);
+              const uint32_t alo_kc = alo + kc * 32;
 #pragma unroll
-              for (int k = 0; k < kKC / 16; ++k) {
-                const uint64_t ad = smem_desc_sw128(a_base + kc * kAChunk + k * 32, 16, 1024);
-                const uint64_t bd = smem_desc_sw128(b_base + k * 32, 16, 1024);
-                mma_f16_ss(d_tmem, ad, bd, kIdescHalf, accumulate);
+              for (int pass = 0; pass < 2; ++pass) {            // sub-chunk: W_hi then W_lo of (layer, h, kc)
+                if (sub == 0) {
+                  PROF3_ACC(5);
+                  mbar_wait(smem_u32(&bars->w_full[stage]), phase);
+                  PROF3_ACC(4);
+                }
+                tc_fence_after_sync();
+                const uint32_t b_lo = smem_desc_lo_sw128(smem_u32(smem + k3SmemW + stage * k3WStage) + sub * k3WSub, 16);
+                if (leader) {
+                  if (pass == 0) {
+#pragma unroll
+                    for (int k = 0; k < kKC / 16; ++k) {
+                      const uint64_t bd = desc_pack(b_lo + 2 * k, kDescHi);
+                      mma_f16_ss(d_tmem, desc_pack(a_kc + 2 * k, kDescHi), bd, kIdescHalf, accumulate | (uint32_t)(k > 0));
+                      if (!(p.dbg & 32)) mma_f16_ts(d_tmem, alo_kc + k * 8, bd, kIdescHalf, 1);
+                    }
+                  } else if (!(p.dbg & 16)) {
+#pragma unroll
+                    for (int k = 0; k < kKC / 16; ++k)
+                      mma_f16_ss(d_tmem, desc_pack(a_kc + 2 * k, kDescHi), desc_pack(b_lo + 2 * k, kDescHi), kIdescHalf, 1);
+                  }
+                }
                 accumulate = 1;
-                mma_f16_ts(d_tmem, alo + kc * 32 + k * 8, bd, kIdescHalf, 1);
+                if (++sub == k3SubPerStage) {
+                  sub = 0;
+                  if (leader) mma_commit(smem_u32(&bars->w_empty[stage]));
+                  if (++stage == k3Stages) { stage = 0; phase ^= 1; }
+                }
               }
-#pragma unroll
-              for (int k = 0; k < kKC / 16; ++k) {
-                const uint64_t ad = smem_desc_sw128(a_base + kc * kAChunk + k * 32, 16, 1024);
-                const uint64_t bd = smem_desc_sw128(b_base + 16384 + k * 32, 16, 1024);
-                mma_f16_ss(d_tmem, ad, bd, kIdescHalf, 1);
-              }
-              mma_commit(smem_u32(&bars->w_empty[stage]));
-              if (++stage == k3Stages) { stage = 0; phase ^= 1; }
             }
-            mma_commit(smem_u32(&bars->acc_full[h]));
-            // the second layer's operand buffer is where the generator writes the next tile's first operand
-            if (layer == 1 && h == 1) mma_commit(smem_u32(&bars->gen_go));
+            if (leader) {
+              mma_commit(smem_u32(&bars->acc_full[h]));
+              // the second layer's operand buffer is where the generator writes the next tile's first operand
+              if (layer == 1 && h == 1) mma_commit(smem_u32(&bars->gen_go));
+            }
+            __syncwarp();
           }
         }
+      if (prof && lane == 0) {
+        for (int c = 0; c < 5; ++c) g_chain_prof[blockIdx.x][c] = pacc[c];
+        g_chain_prof[blockIdx.x][5] = (uint32_t)clock() - t_begin;
+        g_chain_prof[blockIdx.x][13] = my_tiles;
+      }
     }
+  }
   } else if (warp >= 12) {
-    // ================= operand generator =================
-    const int q = warp & 3, gt = threadIdx.x - 384;
+    // ================= operand generator: 8 warps, thread = (row, column half) =================
+    // register pool of the CTA = 640 x 96 at launch: 128 x 48 (control) + 256 x 88 (generator) + 256 x 128 (epilogue) = 61440
+    reg_dec<88>();
+    const int q = warp & 3, ch = (warp - 12) >> 2, gt = threadIdx.x - 384;
     const int row = q * 32 + lane;
     uint32_t swz[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) swz[k] = sw128_offset(row, k * 8);
     uint32_t go_phase = 0;
+    const bool prof = PROF && gt == 0;
+    uint32_t pacc[PROF ? 2 : 1] = {0};
+    PROF3_T0();
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       const int b = tile / p.tiles_per_sample;
       const int pr = (tile % p.tiles_per_sample) * kTileM + row;
       const int a = pr / p.n, c = pr - a * p.n;
       const uint32_t buf = (3u * (uint32_t)i) & 1u;
+      const float4* up = reinterpret_cast<const float4*>(p.U4) + ((size_t)b * (kG / 4) + ch * 32) * p.n + c;      // + g4 * n
+      const float4* vp = reinterpret_cast<const float4*>(p.Vb + ((size_t)b * p.n + a) * kG + ch * 128);
+      float4 u[4], v[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {                      // first 16 columns: in flight while waiting for the buffer
+        u[g] = __ldg(up + (size_t)g * p.n);
+        v[g] = __ldg(vp + g);
+      }
       if (i > 0) {
         mbar_wait(smem_u32(&bars->gen_go), go_phase);
         go_phase ^= 1;
         tc_fence_after_sync();
       }
-      const float4* up = reinterpret_cast<const float4*>(p.U4) + (size_t)b * (kG / 4) * p.n + c;      // + g4 * n
-      const float4* vp = reinterpret_cast<const float4*>(p.Vb + ((size_t)b * p.n + a) * kG);
+      PROF3_ACC(0);
       char* a_dst = smem + buf * kATile;
-      const uint32_t alo = tmem_base + ((uint32_t)(q * 32) << 16) + k3AloCol + buf * 128;
-      uint32_t mw[8];
+      const uint32_t alo = tmem_base + ((uint32_t)(q * 32) << 16) + k3AloCol + buf * 128 + ch * 64;
+      uint32_t* mrow = p.masks + ((size_t)tile * kTileM + row) * 8 + ch * 4;       // masks[0] = M1, same layout as M2..M4
 #pragma unroll 1
-      for (int c64 = 0; c64 < 4; ++c64) {                 // 64 columns = 32 tensor-memory columns per store
-        uint32_t lo[32];
+      for (int cc = 0; cc < 4; ++cc) {                    // 32 columns = 16 tensor-memory columns per store
+        uint32_t lo[16];
+        uint32_t bits = 0;
 #pragma unroll
-        for (int c32 = 0; c32 < 2; ++c32) {
-          const int cc = c64 * 2 + c32;
-          float4 u[8], v[8];
+        for (int h16 = 0; h16 < 2; ++h16) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            u[g] = __ldg(up + (size_t)(cc * 8 + g) * p.n);
-            v[g] = __ldg(vp + cc * 8 + g);
-          }
-          uint32_t bits = 0;
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
+          for (int g8 = 0; g8 < 2; ++g8) {
             const float4 u0 = u[2 * g8], u1 = u[2 * g8 + 1], v0 = v[2 * g8], v1 = v[2 * g8 + 1];
             uint4 o;
-            uint32_t* l4 = lo + c32 * 16 + g8 * 4;
+            uint32_t* l4 = lo + h16 * 8 + g8 * 4;
             split_relu_half2(u0.x + v0.x, u0.y + v0.y, o.x, l4[0]);
             split_relu_half2(u0.z + v0.z, u0.w + v0.w, o.y, l4[1]);
             split_relu_half2(u1.x + v1.x, u1.y + v1.y, o.z, l4[2]);
             split_relu_half2(u1.z + v1.z, u1.w + v1.w, o.w, l4[3]);
             if (SAVE) {
-              bits |= half2_pos_mask(o.x) & mask_pair_const(g8 * 4 + 0);
-              bits |= half2_pos_mask(o.y) & mask_pair_const(g8 * 4 + 1);
-              bits |= half2_pos_mask(o.z) & mask_pair_const(g8 * 4 + 2);
-              bits |= half2_pos_mask(o.w) & mask_pair_const(g8 * 4 + 3);
+              bits |= half2_pos_mask(o.x) & mask_pair_const(h16 * 8 + g8 * 4 + 0);
+              bits |= half2_pos_mask(o.y) & mask_pair_const(h16 * 8 + g8 * 4 + 1);
+              bits |= half2_pos_mask(o.z) & mask_pair_const(h16 * 8 + g8 * 4 + 2);
+              bits |= half2_pos_mask(o.w) & mask_pair_const(h16 * 8 + g8 * 4 + 3);
             }
-            const int col = cc * 32 + g8 * 8;
+            const int col = ch * 128 + cc * 32 + h16 * 16 + g8 * 8;
             *reinterpret_cast<uint4*>(a_dst + (col >> 6) * kAChunk + swz[(col >> 3) & 7]) = o;
           }
-          mw[cc] = bits;
+          const int nxt = cc * 2 + h16 + 1;               // next 16-column block of this thread's 128 columns
+          if (nxt < 8) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              u[g] = __ldg(up + (size_t)(nxt * 4 + g) * p.n);
+              v[g] = __ldg(vp + nxt * 4 + g);
+            }
+          }
         }
-        tmem_st32(alo + c64 * 32, lo);
+        if (SAVE) mrow[cc] = bits;
+        tmem_st16(alo + cc * 16, lo);
       }
       tmem_st_wait();
-      if (SAVE) {
-        uint32_t* mrow = p.masks + ((size_t)tile * kTileM + row) * 8;       // masks[0] = M1, same layout as M2..M4
-        *reinterpret_cast<uint4*>(mrow) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-        *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
-      }
       fence_proxy_async_smem();
       if (SAVE && !p.skip_h1_image) {
-        named_bar_sync(3, 128);
+        named_bar_sync(3, 256);
         if (gt == 0) {
           bulk_s2g(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile, smem_u32(a_dst), kATile);
           bulk_commit();
@@ -1048,17 +1135,26 @@ __global__ void __launch_bounds__(k3Threads, 1) rn_g_fwd3_kernel(const ChainPara
       }
       tc_fence_before_sync();
       mbar_arrive(smem_u32(&bars->gen_ready));
+      PROF3_ACC(1);
+    }
+    if (prof) {
+      g_chain_prof[blockIdx.x][11] = pacc[0];
+      g_chain_prof[blockIdx.x][12] = pacc[1];
     }
     if (SAVE && gt == 0) bulk_wait0();
-  } else if (warp >= 4) {
+  } else {
     // ================= epilogue warps =================
+    reg_inc<128>();
     const int q = warp & 3, ch = (warp - 4) >> 2, et = threadIdx.x - 128;
     const int row = q * 32 + lane;
     uint32_t swz[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) swz[k] = sw128_offset(row, k * 8);
-    uint32_t acc_phase[2] = {0, 0};
+    uint32_t acc_phase = 0, h3_phase = 0;
     uint32_t j = 0;
+    const bool prof = PROF && et == 0;
+    uint32_t pacc[PROF ? 8 : 1] = {0};
+    PROF3_T0();
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       const int b = tile / p.tiles_per_sample;
@@ -1069,12 +1165,15 @@ __global__ void __launch_bounds__(k3Threads, 1) rn_g_fwd3_kernel(const ChainPara
           const int colbase = h * 128 + ch * 64;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + colbase;
           uint32_t* mrow = SAVE ? p.masks + (((size_t)(layer + 1) * p.num_tiles + tile) * kTileM + row) * 8 + (colbase >> 5) : nullptr;
-          mbar_wait(smem_u32(&bars->acc_full[h]), acc_phase[h]);
-          acc_phase[h] ^= 1;
+          mbar_wait(smem_u32(&bars->acc_full[h]), (acc_phase >> h) & 1u);
+          acc_phase ^= 1u << h;
+          PROF3_ACC(h * 2);
           tc_fence_after_sync();
           if (layer < kTcLayers - 1) {
-            // thread 128 has finished waiting for the image store that read this buffer two operands ago
-            if (SAVE && h == 0) named_bar_sync(1, 256);
+            if (SAVE && layer == 0 && h == 0 && i > 0) {      // the previous tile's H3 image store has finished reading this buffer
+              mbar_wait(smem_u32(&bars->h3_done), h3_phase);
+              h3_phase ^= 1;
+            }
             char* a_dst = smem + nbuf * kATile;
             uint32_t lo[32], mw[2];
 #pragma unroll
@@ -1110,15 +1209,8 @@ __global__ void __launch_bounds__(k3Threads, 1) rn_g_fwd3_kernel(const ChainPara
             fence_proxy_async_smem();
             tc_fence_before_sync();
             mbar_arrive(smem_u32(&bars->epi_ready[h]));
-            if (SAVE && h == 1) {
-              named_bar_sync(2, 256);                   // both halves written and fenced by every epilogue thread
-              if (et == 0) {
-                bulk_s2g(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + layer + 1) * kATile, smem_u32(a_dst), kATile);
-                bulk_commit();
-                bulk_wait_read0();
-                if (layer == 0) mbar_arrive(smem_u32(&bars->gen_go));
-              }
-            }
+            if (SAVE && h == 1) mbar_arrive(smem_u32(&bars->img_ready));      // both halves written and fenced by this thread
+            PROF3_ACC(h * 2 + 1);
           } else {
             // last layer: ReLU + pair-sum (column sums over this warp's 32 rows)
             float* part = p.xg_part + ((size_t)tile * 4 + q) * kG;
@@ -1148,11 +1240,12 @@ __global__ void __launch_bounds__(k3Threads, 1) rn_g_fwd3_kernel(const ChainPara
             if (SAVE) *reinterpret_cast<uint2*>(mrow) = make_uint2(mw[0], mw[1]);
             tc_fence_before_sync();
             mbar_arrive(smem_u32(&bars->acc_free[h]));
+            PROF3_ACC(4);
           }
         }
       }
     }
-    if (SAVE && et == 0) bulk_wait0();
+    if (prof) for (int c = 0; c < 5; ++c) g_chain_prof[blockIdx.x][6 + c] = pacc[c];
   }
 
   tc_fence_before_sync();
@@ -1805,8 +1898,13 @@ int tc_relation_fwd(const RelShape& s, int precision, bool training, const float
   p.passes = precision == RN_PRECISION_FAST ? 1 : 2;
   p.U4 = sv.pre.U4;
   if (fwd3) {
-    RN_CUDA(cudaFuncSetAttribute(rn_g_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemLaunch));
-    rn_g_fwd3_kernel<true><<<std::min(p.num_tiles, sm_count()), k3Threads, k3SmemLaunch, st>>>(p);
+    if (p.dbg & 8) {
+      RN_CUDA(cudaFuncSetAttribute(rn_g_fwd3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemLaunch));
+      rn_g_fwd3_kernel<true, true><<<std::min(p.num_tiles, sm_count()), k3Threads, k3SmemLaunch, st>>>(p);
+    } else {
+      RN_CUDA(cudaFuncSetAttribute(rn_g_fwd3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemLaunch));
+      rn_g_fwd3_kernel<true, false><<<std::min(p.num_tiles, sm_count()), k3Threads, k3SmemLaunch, st>>>(p);
+    }
     RN_LAUNCH_CHECK("rn_g_fwd3_kernel");
   } else if (training) {
     RN_TRY(launch_chain<kFwdTrain>(p, st));

@@ -21,12 +21,21 @@ CASES = {
 }
 
 
+# round-2 training fixtures (no *_eval twin): batch 32 and the d = 16 grid
+TRAIN_ONLY_CASES = {
+    "ckpt_original_fp_b32": ("original-fp", "ckpt_original_fp_eval"),
+    "seeded_original_fp_b32": ("original-fp", 401),
+    "seeded_ir_fp_b32": ("ir-fp", 411),
+    "seeded_original_fp_d16": ("original-fp", 421),
+}
+
+
 def load_npz(name):
     return np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
 
 
 def case_params(stem, dtype=torch.float32):
-    config, src = CASES[stem]
+    config, src = CASES[stem] if stem in CASES else TRAIN_ONLY_CASES[stem]
     hyp = O.HYPERPARAMS[config]
     if isinstance(src, int):
         return hyp, O.seeded_params(hyp, QDICT, ADICT, src, dtype)

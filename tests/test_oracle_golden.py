@@ -5,12 +5,12 @@ import torch
 import torch.nn.functional as F
 
 from oracle import rn_oracle as O
-from tests.golden_util import CASES, case_inputs, case_params, golden_grad_check, load_npz
+from tests.golden_util import CASES, TRAIN_ONLY_CASES, case_inputs, case_params, golden_grad_check, load_npz
 
 TOL = 2e-5      # fp32 vs fp32, different summation order only
 
 EVAL_CASES = [s for s in CASES]
-TRAIN_CASES = [s for s in CASES if s != "seeded_original_fp_d12"]
+TRAIN_CASES = [s for s in CASES if s != "seeded_original_fp_d12"] + list(TRAIN_ONLY_CASES)
 
 
 @pytest.mark.parametrize("stem", EVAL_CASES)
@@ -44,7 +44,9 @@ def test_train_step_matches_reference(stem):
     n = 0
     for k, v in leaves.items():
         if f"grad/{k}/l2" in z.files:
-            golden_grad_check(z, k, v.grad, 3e-4, errs)   # fp32 vs fp32 through 4 BN layers
+            # fp32 vs fp32 through 4 BN layers: two fp32 evaluation orders already disagree on a few ReLU masks;
+            # measured <= 3e-4 on the batch-4 fixtures, 3.5e-4 on the batch-32 checkpoint fixture
+            golden_grad_check(z, k, v.grad, 3e-4 if stem in CASES else 6e-4, errs)
             n += 1
     assert n >= (19 if hyp["state_description"] else 35)
     for k, v in running.items():
