@@ -12,7 +12,7 @@ import torch.nn.functional as F
 import relationnetworks_clevr_b200 as R
 from oracle import rn_oracle as O
 from relationnetworks_clevr_b200 import ops
-from tests.golden_util import CASES, case_inputs, case_params, load_npz, oracle_train_grads
+from tests.golden_util import CASES, TRAIN_ONLY_CASES, case_inputs, case_params, load_npz, oracle_train_grads
 
 pytestmark = pytest.mark.gpu
 
@@ -90,14 +90,16 @@ def test_relation_fp32_matches_oracle(name):
     _relation_case(name, "fp32", TOL_FP32)
 
 
-# tcgen05 path.  Forward (the north-star bar): 1e-3 max-norm vs the fp64 oracle -- measured ~1e-5.
-# Backward: the kernels return the exact gradient of the network they ran forward, i.e. with fp16-rounded
-# activations.  Rounding an activation (2^-11 relative) flips the sign of pre-activations that sit within
-# ~1e-4 of zero in the next layer; each flip switches one ReLU-mask entry relative to the fp32 reference.
-# That is zero-mean noise: it averages out in parameter gradients (sums over all pairs and samples) and is
-# largest in the per-object input gradient dx (64 x 256 contributions).  Tolerances (max-norm, L2-relative):
-TOL_TC_PARAM = (6e-3, 6e-3)      # dW, db, dq at >= 8k pair rows; measured 2e-4 .. 4e-3
-TOL_TC_DX = (2.5e-2, 1.2e-2)     # measured 5e-3 .. 1.4e-2 / 4e-3 .. 8e-3
+# tcgen05 path.  Forward (the north-star bar): 1e-3 max-norm vs the fp64 oracle -- measured ~1e-6 .. 1e-5.
+# Backward, "parity" mode: the training forward computes every pre-activation as A_hi W_hi + A_lo W_hi + A_hi W_lo (fp16
+# splits of activations AND weights, fp32 accumulate), so its ReLU masks agree with an fp32 evaluation; what is left is the
+# fp16 rounding of the dZ operands (2^-11 relative, zero mean).  Bars (max-norm, L2-relative), floored like the fp32 tests at
+# 4x the fp32-oracle-vs-fp64-oracle distance: dW / db / dq 1e-3; the per-object input gradient dx (a sum of only
+# 128 x 256 terms, whose fp32-vs-fp64 distance is itself ~2e-3 on these inputs) 6e-3 / 1.5e-3.
+# "fast" mode (one fp16 pass everywhere, fp16 activations): ~1e-4 of the ReLU masks differ from fp32, which shows as
+# 2e-4 .. 4e-3 on parameter gradients and 5e-3 .. 2e-2 on dx whatever the batch size (profiles/r02_grad_error_vs_batch.json).
+TOL_TC_PARAM = {"parity": (1e-3, 1e-3), "fast": (6e-3, 6e-3)}
+TOL_TC_DX = {"parity": (6e-3, 1.5e-3), "fast": (2.5e-2, 1.2e-2)}
 TC_CASES = {
     # name: (B, n, qinj)
     "fp_d4_b32": (32, 16, 0),
@@ -118,6 +120,8 @@ def test_relation_tcgen05_matches_oracle(name, precision):
     gp = _g_params(n, k, Q, G, qinj, gen, scale=2.0)
     dxg = torch.randn(B, G, generator=gen)
     ref = _oracle_grads(x, q, gp, qinj, dxg, torch.float64)
+    ref32 = _oracle_grads(x, q, gp, qinj, dxg, torch.float32)
+    floor = {k_: 4 * O.rel_err(ref32[k_], ref[k_]) for k_ in ref}
     xc, qc = x.to(DEV).requires_grad_(True), q.to(DEV).requires_grad_(True)
     wb = []
     for w, b in gp:
@@ -137,9 +141,9 @@ def test_relation_tcgen05_matches_oracle(name, precision):
     for k_, (emax, el2) in errs.items():
         if k_ == "xg":
             continue
-        tmax, tl2 = TOL_TC_DX if k_ == "dx" else TOL_TC_PARAM
-        if emax > tmax or el2 > tl2:
-            bad[k_] = (emax, el2)
+        tmax, tl2 = (TOL_TC_DX if k_ == "dx" else TOL_TC_PARAM)[precision]
+        if emax > max(tmax, floor[k_]) or el2 > max(tl2, floor[k_]):
+            bad[k_] = (emax, el2, floor[k_])
     assert not bad, bad
 
 
@@ -167,6 +171,48 @@ def test_relation_tcgen05_backward_is_linear_in_dxg():
     with torch.no_grad():
         ref = ops.RelationFunction.apply(x, q, qinj, "fp32", *wb)
     assert O.rel_err(xg.detach().cpu(), ref.cpu()) < TOL_PARITY
+
+
+@pytest.mark.parametrize("stem", ["seeded_original_fp", "ckpt_original_fp"])
+def test_gradient_parity_at_bench_shape(stem):
+    """The benchmarked configuration (BASELINE.json config 2: original-fp, d = 8, B = 640, train mode, parity precision):
+    gradients of all 35 parameter tensors and of the relation op's inputs against this library's fp32 SIMT path, which
+    the tests above pin to the CPU oracle at 2e-4.  Bar: 1e-3 max-norm for every parameter gradient and dq (measured
+    3e-4 .. 6e-4, profiles/r02_grad_error_vs_batch.json); dx: 1.5e-3 in L2 (max-norm 6e-3: the fp32 conditioning of a
+    128 x 256-term sum)."""
+    hyp, p = case_params(stem)
+    B = 640
+    img = O.structured_images(B, 128, 7).to(DEV)
+    qst = O.questions(B, 20, 82, 8).to(DEV)
+    lab = O.labels(B, 28, 9).to(DEV)
+    mask = (torch.rand(B, hyp["f_fc2"], generator=torch.Generator().manual_seed(10)) > 0.5).to(torch.uint8)
+    res = {}
+    for precision in ("fp32", "parity"):
+        m = R.RN(_Args, hyp)
+        m.load_state_dict(p, strict=False)
+        m.to(DEV).train()
+        m.rl.precision = precision
+        m.rl.dropout_mask_override = mask
+        x = m.conv.objects(img)
+        q = m.text(qst)
+        x.retain_grad()
+        q.retain_grad()
+        logp = m.rl(x, q)
+        F.nll_loss(logp, lab).backward()
+        out = {"logp": logp.detach(), "dx": x.grad, "dq": q.grad}
+        out.update({n_: prm.grad for n_, prm in m.named_parameters()})
+        res[precision] = {k_: v.double().cpu() for k_, v in out.items()}
+        del m
+    bad = {}
+    for k_, ref in res["fp32"].items():
+        if k_.startswith("conv.conv") and k_.endswith("bias"):
+            continue
+        d = res["parity"][k_] - ref
+        emax, el2 = float(d.abs().max() / ref.abs().max()), float(d.norm() / ref.norm())
+        tmax, tl2 = (6e-3, 1.5e-3) if k_ == "dx" else (1e-3, 1e-3)
+        if emax > tmax or el2 > tl2:
+            bad[k_] = (emax, el2)
+    assert not bad, bad
 
 
 def test_relation_eval_forward_and_determinism():
@@ -295,7 +341,7 @@ def test_model_eval_matches_reference_golden(stem, precision):
     assert torch.equal(logp.argmax(1), torch.from_numpy(z["logp"]).argmax(1))
 
 
-@pytest.mark.parametrize("stem", [s for s in CASES if s != "seeded_original_fp_d12"])
+@pytest.mark.parametrize("stem", [s for s in CASES if s != "seeded_original_fp_d12"] + list(TRAIN_ONLY_CASES))
 @pytest.mark.parametrize("precision", ["fp32", "auto"])
 def test_model_train_step_matches_reference_golden(stem, precision):
     z = load_npz(stem + "_train")
@@ -320,10 +366,12 @@ def test_model_train_step_matches_reference_golden(stem, precision):
             assert float(prm.grad.abs().max()) == 0.0       # exactly zero under batch statistics
             continue
         err = O.rel_err(prm.grad.cpu(), ref[name])
-        tc = m.rl._resolve_precision(64, 26) != "fp32" and not hyp["state_description"]
-        # tcgen05 modes: gradients are those of the fp16-activation network (see TOL_TC_* above); at this
-        # batch of 4 the ReLU-mask noise is not averaged down, the sparse trained checkpoints being the worst
-        gtol = 8e-2 if tc else max(tol, 8 * floor[name])
+        # parity mode (3-pass forward: fp32-level ReLU masks) holds the same kind of bar as the fp32 kernels: 1e-3
+        # (2e-4 for fp32) floored at 8x the fp32-oracle-vs-fp64-oracle distance of the same tensor on the same inputs.
+        # Batch-32 / d = 16 fixtures: 2e-3 for BOTH precisions -- measured worst case 1.2e-3 (fp32 SIMT kernels) and
+        # 1.3e-3 (parity) on the trained checkpoint, whose gradients are the least well conditioned (any two fp32
+        # evaluation orders disagree on a few ReLU masks; tests/diag_golden_errors.py prints the per-tensor numbers)
+        gtol = max(tol if stem in CASES else 2e-3, 8 * floor[name])
         if err > gtol:
             bad[name] = (err, floor[name])
     assert not bad, bad
@@ -354,9 +402,15 @@ def test_relation_tcgen05_grid_sweep(n):
         xg.backward(dxg)
         res[precision] = [xg.detach(), xc.grad, qc.grad] + [t.grad for t in wb]
     assert O.rel_err(res["parity"][0].cpu(), res["fp32"][0].cpu()) < TOL_PARITY
-    assert O.rel_err(res["parity"][1].cpu(), res["fp32"][1].cpu()) < TOL_TC_DX[0]
+    assert O.rel_err(res["parity"][1].cpu(), res["fp32"][1].cpu()) < TOL_TC_DX["parity"][0]
     for a, b_ in zip(res["parity"][2:], res["fp32"][2:]):
-        assert O.rel_err(a.cpu(), b_.cpu()) < TOL_TC_PARAM[0]
+        assert O.rel_err(a.cpu(), b_.cpu()) < TOL_TC_PARAM["parity"][0]
+    # ... and against the CPU oracle (fp64, materialised pairs: 2 x n^2 rows fit on the host at this batch)
+    ref = _oracle_grads(x.cpu(), q.cpu(), params, qinj, dxg.cpu(), torch.float64)
+    names = ["xg", "dx", "dq"] + [f"d{t}{l}" for l in range(4) for t in ("W", "b")]
+    for nm, got in zip(names, res["parity"]):
+        tol = TOL_PARITY if nm == "xg" else (TOL_TC_DX if nm == "dx" else TOL_TC_PARAM)["parity"][0]
+        assert O.rel_err(got.cpu(), ref[nm]) < tol, (nm, O.rel_err(got.cpu(), ref[nm]))
 
 
 def test_train_driver_smoke(tmp_path):
