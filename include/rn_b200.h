@@ -170,6 +170,30 @@ typedef struct rn_conv_grads {
 int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float* dobjects, const rn_conv_layer* h_layers,
                 const float* saved, const rn_conv_grads* h_grads, float* scratch, void* stream);
 
+/* ---- question encoder: Embedding -> 1-layer LSTM (zero initial state) -> last hidden state (model.py:39-58) ---- */
+typedef struct rn_lstm_cfg {
+  int32_t B;         /* questions */
+  int32_t T;         /* tokens per question (<= 64) */
+  int32_t V;         /* embedding rows (qdict_size + 1); token ids are clamped to [0, V) */
+  int32_t E;         /* embedding width (hyp["lstm_word_emb"]) */
+  int32_t H;         /* hidden size (hyp["lstm_hidden"]); the kernels exist for H == 128 */
+  int32_t training;  /* 1: keep what rn_lstm_bwd needs in `saved` */
+} rn_lstm_cfg;
+
+/* 1 when the kernels support this shape (H == 128, T <= 64); the host keeps torch's nn.LSTM otherwise. */
+int rn_lstm_supported(const rn_lstm_cfg* cfg);
+int rn_lstm_workspace(const rn_lstm_cfg* cfg, size_t* saved_floats, size_t* scratch_floats);
+
+/* tokens [B, T] int64 (as the reference feeds nn.Embedding); emb [V, E]; w_ih [4H, E], w_hh [4H, H], b_ih / b_hh [4H]
+ * exactly as text.lstm.{weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0} (gate order i, f, g, o).  q [B, H] out. */
+int rn_lstm_fwd(const rn_lstm_cfg* cfg, const int64_t* tokens, const float* emb, const float* w_ih, const float* w_hh,
+                const float* b_ih, const float* b_hh, float* q, float* saved, void* stream);
+
+/* dq [B, H] in; all five gradients are OVERWRITTEN (embedding rows of unused tokens receive zeros). */
+int rn_lstm_bwd(const rn_lstm_cfg* cfg, const int64_t* tokens, const float* emb, const float* w_ih, const float* w_hh,
+                const float* dq, const float* saved, float* demb, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                float* scratch, void* stream);
+
 /* ---- optimiser tail: clip_grad_norm + Adam with L2 weight decay (train.py:45-48,330) on flat buffers ---- */
 typedef struct rn_adam_cfg {
   int64_t n;          /* elements in the flat parameter / gradient buffers */

@@ -42,6 +42,10 @@ class ConvGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("dw", "dbias", "dgamma", "dbeta")]
 
 
+class LstmCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "T", "V", "E", "H", "training")]
+
+
 class AdamCfg(C.Structure):
     _fields_ = [("n", C.c_int64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float), ("clip_norm", C.c_float), ("grad_scale", C.c_float), ("step", C.c_int32)]
@@ -64,6 +68,10 @@ SIGNATURES = {
     "rn_conv_workspace": (C.c_int, [C.POINTER(ConvCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "rn_conv_fwd": (C.c_int, [C.POINTER(ConvCfg), _P, C.POINTER(ConvLayer), _P, _P, _P, _P]),
     "rn_conv_bwd": (C.c_int, [C.POINTER(ConvCfg), _P, _P, C.POINTER(ConvLayer), _P, C.POINTER(ConvGrads), _P, _P]),
+    "rn_lstm_supported": (C.c_int, [C.POINTER(LstmCfg)]),
+    "rn_lstm_workspace": (C.c_int, [C.POINTER(LstmCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "rn_lstm_fwd": (C.c_int, [C.POINTER(LstmCfg)] + [_P] * 9),
+    "rn_lstm_bwd": (C.c_int, [C.POINTER(LstmCfg)] + [_P] * 13),
     "rn_clip_adam": (C.c_int, [C.POINTER(AdamCfg), _P, _P, _P, _P, _P, _P, _P]),
 }
 

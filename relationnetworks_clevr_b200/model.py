@@ -67,10 +67,18 @@ class QuestionEmbedModel(nn.Module):
         self.wembedding = nn.Embedding(in_size + 1, embed)
         self.lstm = nn.LSTM(embed, hidden, batch_first=True)
         self.hidden = hidden
+        self.use_kernel = os.environ.get("RN_B200_LSTM_KERNEL", "1") != "0"
 
     def forward(self, question: torch.Tensor) -> torch.Tensor:
+        if self.use_kernel and question.is_cuda and question.dim() == 2 and ops.lstm_supported(
+                question.shape[0], question.shape[1], self.wembedding.num_embeddings, self.wembedding.embedding_dim, self.hidden):
+            # one persistent launch for all T steps (csrc/lstm.cu); the nn.LSTM module only holds the parameters
+            return ops.QuestionEncoderFunction.apply(question, self.wembedding.weight, self.lstm.weight_ih_l0,
+                                                     self.lstm.weight_hh_l0, self.lstm.bias_ih_l0, self.lstm.bias_hh_l0)
+        # other shapes (hidden size 256 of the state-description configs, T > 64): PyTorch / cuDNN, fp32 (TF32 off, see __init__)
         wembed = self.wembedding(question)
-        _, hidden = self.lstm(wembed)      # fp32: the package turns cuDNN TF32 off at import (see __init__)
+        self.lstm.flatten_parameters()
+        _, hidden = self.lstm(wembed)
         return hidden[0][0]
 
 
@@ -174,7 +182,9 @@ class RN(nn.Module):
     def forward(self, img: torch.Tensor, qst_idxs: torch.Tensor):
         if not img.is_cuda:
             raise RuntimeError("RN (B200-native) needs CUDA inputs: call model.cuda() and move the batch to the GPU")
-        if self.state_desc or os.environ.get("RN_B200_TEXT_STREAM", "1") == "0":
+        if self.state_desc or os.environ.get("RN_B200_TEXT_STREAM", "1") == "0" or (self.text.use_kernel and self.text.hidden == 128):
+            # (the question-encoder kernel is one short launch: nothing to gain from a side stream, and the step stays
+            # a single-stream sequence that CUDA-graph capture takes as is)
             x = img if self.state_desc else self.conv.objects(img)
             qst = self.text(qst_idxs)
             return self.rl(x, qst)

@@ -12,7 +12,7 @@ from typing import Dict, Tuple
 import torch
 
 from . import _lib
-from ._lib import PRECISION, AdamCfg, ConvCfg, ConvGrads, ConvLayer, FCfg, RelationCfg, check, lib, ptr_array
+from ._lib import PRECISION, AdamCfg, ConvCfg, ConvGrads, ConvLayer, FCfg, LstmCfg, RelationCfg, check, lib, ptr_array
 
 _scratch: Dict[Tuple[int, str], torch.Tensor] = {}
 
@@ -86,6 +86,51 @@ def timers_collect() -> Dict[str, list]:
     return {k: [a.elapsed_time(b) for a, b in v] for k, v in _timer_events.items()}
 
 
+# ---- gradient sink: parameter gradients written straight into the optimiser's flat gradient buffer ----------------
+# trainer.FlatClipAdam keeps every parameter as a view of ONE flat fp32 buffer.  While a sink is registered, the backward
+# of each op writes the gradient of such a parameter directly into the matching slice of the flat GRADIENT buffer and
+# returns None for it to autograd (param.grad stays None): no per-parameter gradient tensors, no torch.cat, no zero
+# fills -- every slice is overwritten by exactly one kernel per step.  Without a sink the ops return ordinary tensors.
+_sink = None      # (flat_params, flat_grads)
+
+
+def set_grad_sink(flat_params: torch.Tensor, flat_grads: torch.Tensor) -> None:
+    global _sink
+    if flat_params.numel() != flat_grads.numel() or flat_params.dtype != torch.float32 or flat_grads.dtype != torch.float32:
+        raise RuntimeError("gradient sink: flat parameter and gradient buffers must be fp32 and equally long")
+    _sink = (flat_params, flat_grads)
+
+
+def clear_grad_sink() -> None:
+    global _sink
+    _sink = None
+
+
+def _sink_view(p: torch.Tensor):
+    if _sink is None or not p.is_contiguous() or p.dtype != torch.float32:
+        return None
+    flat, grads = _sink
+    if p.device != flat.device:
+        return None
+    off = p.data_ptr() - flat.data_ptr()
+    if off < 0 or off % 4 or off // 4 + p.numel() > flat.numel():
+        return None
+    return grads[off // 4: off // 4 + p.numel()].view(p.shape)
+
+
+def _grad_outputs(params, like):
+    """One output tensor per parameter: its slice of the flat gradient buffer when a sink covers it, else a new tensor."""
+    out = []
+    for p, l in zip(params, like):
+        v = _sink_view(p)
+        out.append(v if v is not None else torch.empty_like(l))
+    return out
+
+
+def _grad_returns(params, grads):
+    return [None if _sink_view(p) is not None else g for p, g in zip(params, grads)]
+
+
 def _require_cuda(*tensors) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -151,6 +196,7 @@ class RelationFunction(torch.autograd.Function):
             ctx.cfg = cfg
             ctx.saved_buf = saved
             ctx.L = L
+            ctx.params = (wb[0::2], wb[1::2])
             ctx.save_for_backward(x_, q_, *ws)
         return xg
 
@@ -161,8 +207,9 @@ class RelationFunction(torch.autograd.Function):
         dxg_ = _f32c(dxg)
         dx = torch.empty_like(x_)
         dq = torch.empty_like(q_)
-        dws = [torch.empty_like(w) for w in ws]
-        dbs = [torch.empty(w.shape[0], dtype=torch.float32, device=x_.device) for w in ws]
+        pw, pb = ctx.params
+        dws = _grad_outputs(pw, ws)
+        dbs = _grad_outputs(pb, [torch.empty(w.shape[0], dtype=torch.float32, device=x_.device) for w in ws])
         sb, cb = C.c_size_t(), C.c_size_t()
         check(lib().rn_relation_workspace(C.byref(cfg), C.byref(sb), C.byref(cb)), "rn_relation_workspace")
         scratch = _scratch_bytes(x_.device, "relation", cb.value)
@@ -172,7 +219,7 @@ class RelationFunction(torch.autograd.Function):
                                         ptr_array(dbs), scratch.data_ptr(), _stream()), "rn_relation_bwd")
         _mark_for_side_consumers(dq)
         grads = []
-        for dw, db in zip(dws, dbs):
+        for dw, db in zip(_grad_returns(pw, dws), _grad_returns(pb, dbs)):
             grads += [dw, db]
         return (dx, dq, None, None, *grads)
 
@@ -199,6 +246,7 @@ class FHeadFunction(torch.autograd.Function):
                                  _stream()), "rn_f_fwd")
         ctx.cfg = cfg
         ctx.has_mask = drop_mask is not None
+        ctx.params = (w1, b1, w2, b2, w3, b3)
         ctx.save_for_backward(logp, saved, t[0], t[1], t[3], t[5], drop_mask if drop_mask is not None else logp)
         return logp
 
@@ -209,16 +257,64 @@ class FHeadFunction(torch.autograd.Function):
         dev = xg.device
         dl = _f32c(dlogp)
         dxg = torch.empty_like(xg)
-        dw1, dw2, dw3 = torch.empty_like(w1), torch.empty_like(w2), torch.empty_like(w3)
-        db1 = torch.empty(cfg.F1, dtype=torch.float32, device=dev)
-        db2 = torch.empty(cfg.F2, dtype=torch.float32, device=dev)
-        db3 = torch.empty(cfg.A, dtype=torch.float32, device=dev)
+        like = [w1, torch.empty(cfg.F1, dtype=torch.float32, device=dev), w2, torch.empty(cfg.F2, dtype=torch.float32, device=dev),
+                w3, torch.empty(cfg.A, dtype=torch.float32, device=dev)]
+        dw1, db1, dw2, db2, dw3, db3 = _grad_outputs(ctx.params, like)
         scratch = torch.empty(cfg.B * (cfg.A + cfg.F2 + cfg.F1), dtype=torch.float32, device=dev)
         check(lib().rn_f_bwd(C.byref(cfg), dl.data_ptr(), logp.data_ptr(), xg.data_ptr(), w1.data_ptr(), w2.data_ptr(),
                              w3.data_ptr(), mask.data_ptr() if ctx.has_mask else None, saved.data_ptr(),
                              dxg.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(),
                              dw3.data_ptr(), db3.data_ptr(), scratch.data_ptr(), _stream()), "rn_f_bwd")
-        return dxg, dw1, db1, dw2, db2, dw3, db3, None, None
+        return (dxg, *_grad_returns(ctx.params, [dw1, db1, dw2, db2, dw3, db3]), None, None)
+
+
+def lstm_supported(B: int, T: int, V: int, E: int, H: int) -> bool:
+    cfg = LstmCfg(B, T, V, E, H, 0)
+    return bool(lib().rn_lstm_supported(C.byref(cfg)))
+
+
+class QuestionEncoderFunction(torch.autograd.Function):
+    """q = last hidden state of LSTM(Embedding(tokens)) with a zero initial state (reference model.py:47-58).
+
+    forward(tokens [B,T] int64, emb [V,E], w_ih [4H,E], w_hh [4H,H], b_ih [4H], b_hh [4H]) -> q [B,H]"""
+
+    @staticmethod
+    def forward(ctx, tokens, emb, w_ih, w_hh, b_ih, b_hh):
+        _require_cuda(tokens, emb, w_ih, w_hh, b_ih, b_hh)
+        if tokens.dtype != torch.int64:
+            raise RuntimeError("question tokens must be int64 (as for nn.Embedding)")
+        tok = tokens.contiguous()
+        ps = [_f32c(t) for t in (emb, w_ih, w_hh, b_ih, b_hh)]
+        B, T = tok.shape
+        V, E = ps[0].shape
+        H = ps[2].shape[1]
+        training = any(ctx.needs_input_grad)
+        cfg = LstmCfg(B, T, V, E, H, int(training))
+        sf, cf = C.c_size_t(), C.c_size_t()
+        check(lib().rn_lstm_workspace(C.byref(cfg), C.byref(sf), C.byref(cf)), "rn_lstm_workspace")
+        saved = torch.empty(sf.value, dtype=torch.float32, device=tok.device)
+        q = torch.empty(B, H, dtype=torch.float32, device=tok.device)
+        with _Timed("lstm_fwd"):
+            check(lib().rn_lstm_fwd(C.byref(cfg), tok.data_ptr(), *[p.data_ptr() for p in ps], q.data_ptr(), saved.data_ptr(),
+                                    _stream()), "rn_lstm_fwd")
+        if training:
+            ctx.cfg = cfg
+            ctx.scratch_floats = cf.value
+            ctx.params = (emb, w_ih, w_hh, b_ih, b_hh)
+            ctx.save_for_backward(tok, saved, *ps)
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        tok, saved, *ps = ctx.saved_tensors
+        dq_ = _f32c(dq)
+        grads = _grad_outputs(ctx.params, ps)
+        scratch = _scratch_bytes(tok.device, "lstm", ctx.scratch_floats * 4)
+        with _Timed("lstm_bwd"):
+            check(lib().rn_lstm_bwd(C.byref(ctx.cfg), tok.data_ptr(), ps[0].data_ptr(), ps[1].data_ptr(), ps[2].data_ptr(),
+                                    dq_.data_ptr(), saved.data_ptr(), *[g.data_ptr() for g in grads], scratch.data_ptr(),
+                                    _stream()), "rn_lstm_bwd")
+        return (None, *_grad_returns(ctx.params, grads))
 
 
 def _conv_layers(params, running) -> C.Array:
@@ -264,6 +360,7 @@ class ConvObjectsFunction(torch.autograd.Function):
             ctx.saved_buf = saved
             ctx.running = running
             ctx.scratch_floats = cf.value
+            ctx.params = params
             ctx.save_for_backward(img_, *ps)
         return objects
 
@@ -272,7 +369,7 @@ class ConvObjectsFunction(torch.autograd.Function):
         img_, *ps = ctx.saved_tensors
         cfg = ctx.cfg
         dobj = _f32c(dobjects)
-        grads = [torch.empty_like(p) for p in ps]
+        grads = _grad_outputs(ctx.params, ps)
         garr = (ConvGrads * 4)()
         for l in range(4):
             garr[l] = ConvGrads(*[g.data_ptr() for g in grads[4 * l: 4 * l + 4]])
@@ -281,7 +378,7 @@ class ConvObjectsFunction(torch.autograd.Function):
         with _Timed("conv_bwd"):
             check(lib().rn_conv_bwd(C.byref(cfg), img_.data_ptr(), dobj.data_ptr(), layers, ctx.saved_buf.data_ptr(),
                                     garr, scratch.data_ptr(), _stream()), "rn_conv_bwd")
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, *_grad_returns(ctx.params, grads))
 
 
 def clip_adam_(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,

@@ -260,6 +260,32 @@ def test_f_head_matches_oracle(dims, use_mask):
         assert O.rel_err(pc[k_].grad.cpu(), p64[k_].grad) < TOL_FP32, k_
 
 
+@pytest.mark.parametrize("B,T", [(3, 5), (37, 20), (80, 45), (640, 20)])
+def test_question_encoder_matches_oracle(B, T):
+    """Embedding + LSTM kernels (csrc/lstm.cu) against the oracle's explicit recurrence in fp64: q and all five gradients."""
+    hyp = O.HYPERPARAMS["original-fp"]
+    p = {k_: v for k_, v in O.seeded_params(hyp, 82, 28, seed=B + T).items() if k_.startswith("text.")}
+    qst = O.questions(B, T, 82, seed=T, left_pad=min(3, T - 1))
+    dq = torch.randn(B, 128, generator=torch.Generator().manual_seed(B))
+    p64 = {k_: v.double().requires_grad_(True) for k_, v in p.items()}
+    ref = O.question_embed(p64, qst)
+    ref.backward(dq.double())
+    m = R.QuestionEmbedModel(82, embed=32, hidden=128)
+    m.load_state_dict({k_[len("text."):]: v for k_, v in p.items()})
+    m.to(DEV)
+    assert m.use_kernel and ops.lstm_supported(B, T, 83, 32, 128)
+    q = m(qst.to(DEV))
+    q.backward(dq.to(DEV))
+    assert O.rel_err(q.detach().cpu(), ref.detach()) < TOL_FP32
+    for name, prm in m.named_parameters():
+        assert O.rel_err(prm.grad.cpu(), p64["text." + name].grad) < TOL_FP32, name
+    # the PyTorch path (kept for other hidden sizes) agrees too
+    m.use_kernel = False
+    m.zero_grad()
+    q2 = m(qst.to(DEV))
+    assert O.rel_err(q2.detach().cpu(), ref.detach()) < TOL_FP32
+
+
 def _conv_params(seed):
     p = O.seeded_params(O.HYPERPARAMS["original-fp"], 82, 28, seed)
     return {k_: v for k_, v in p.items() if k_.startswith("conv.")}
