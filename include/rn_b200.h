@@ -203,9 +203,11 @@ typedef struct rn_adam_cfg {
   int32_t step;       /* 1-based Adam step */
 } rn_adam_cfg;
 
-/* norm_scratch: >= 1024 floats + 1.  total_norm_out (device, 1 float) receives the pre-clip norm. */
+/* norm_scratch: >= 1024 floats + 1.  total_norm_out (device, 1 float) receives the pre-clip norm.
+ * d_step / d_lr (device, optional): when non-NULL the kernels increment *d_step and use it as the Adam step, and read the
+ * learning rate from *d_lr, instead of cfg->step / cfg->lr -- so a CUDA graph captured once replays correct steps. */
 int rn_clip_adam(const rn_adam_cfg* cfg, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                 float* norm_scratch, float* total_norm_out, void* stream);
+                 float* norm_scratch, float* total_norm_out, int32_t* d_step, const float* d_lr, void* stream);
 
 #ifdef __cplusplus
 }

@@ -72,7 +72,7 @@ SIGNATURES = {
     "rn_lstm_workspace": (C.c_int, [C.POINTER(LstmCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "rn_lstm_fwd": (C.c_int, [C.POINTER(LstmCfg)] + [_P] * 9),
     "rn_lstm_bwd": (C.c_int, [C.POINTER(LstmCfg)] + [_P] * 13),
-    "rn_clip_adam": (C.c_int, [C.POINTER(AdamCfg), _P, _P, _P, _P, _P, _P, _P]),
+    "rn_clip_adam": (C.c_int, [C.POINTER(AdamCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -11,8 +11,9 @@ namespace rn {
 constexpr int kNormBlocks = 1024;
 
 __global__ void __launch_bounds__(256)
-sumsq_partial_kernel(const float* __restrict__ g, long long n, float scale, float* __restrict__ part) {
+sumsq_partial_kernel(const float* __restrict__ g, long long n, float scale, float* __restrict__ part, int* __restrict__ d_step) {
   __shared__ double red[8];
+  if (d_step && blockIdx.x == 0 && threadIdx.x == 0) *d_step += 1;      // device-side step counter (CUDA-graph replays)
   double s = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double v = (double)g[i] * scale;
@@ -30,8 +31,11 @@ sumsq_partial_kernel(const float* __restrict__ g, long long n, float scale, floa
 
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(rn_adam_cfg c, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                 float* __restrict__ v, const float* __restrict__ part, float* __restrict__ total_norm_out) {
+                 float* __restrict__ v, const float* __restrict__ part, float* __restrict__ total_norm_out,
+                 const int* __restrict__ d_step, const float* __restrict__ d_lr) {
   __shared__ float coef_s;
+  if (d_step) c.step = *d_step;
+  if (d_lr) c.lr = *d_lr;
   if (threadIdx.x < 32) {
     double s = 0.0;
     for (int i = threadIdx.x; i < kNormBlocks; i += 32) s += part[i];
@@ -64,14 +68,14 @@ clip_adam_kernel(rn_adam_cfg c, float* __restrict__ p, const float* __restrict__
 using namespace rn;
 
 extern "C" int rn_clip_adam(const rn_adam_cfg* cfg, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                            float* norm_scratch, float* total_norm_out, void* stream) {
-  RN_CHECK_ARG(cfg != nullptr && cfg->n > 0 && cfg->step >= 1, "bad adam cfg");
+                            float* norm_scratch, float* total_norm_out, int32_t* d_step, const float* d_lr, void* stream) {
+  RN_CHECK_ARG(cfg != nullptr && cfg->n > 0 && (cfg->step >= 1 || d_step != nullptr), "bad adam cfg");
   RN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && norm_scratch, "NULL pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  sumsq_partial_kernel<<<kNormBlocks, 256, 0, st>>>(grads, cfg->n, cfg->grad_scale, norm_scratch);
+  sumsq_partial_kernel<<<kNormBlocks, 256, 0, st>>>(grads, cfg->n, cfg->grad_scale, norm_scratch, d_step);
   RN_LAUNCH_CHECK("sumsq_partial_kernel");
   const int blocks = (int)std::min<long long>((cfg->n + 255) / 256, 4LL * sm_count());
-  clip_adam_kernel<<<blocks, 256, 0, st>>>(*cfg, params, grads, exp_avg, exp_avg_sq, norm_scratch, total_norm_out);
+  clip_adam_kernel<<<blocks, 256, 0, st>>>(*cfg, params, grads, exp_avg, exp_avg_sq, norm_scratch, total_norm_out, d_step, d_lr);
   RN_LAUNCH_CHECK("clip_adam_kernel");
   return RN_OK;
 }

@@ -48,8 +48,8 @@ class ConvInputModel(nn.Module):
         for conv, bn in self._layers():
             params += [conv.weight, conv.bias, bn.weight, bn.bias]
             running += [bn.running_mean, bn.running_var]
-            if self.training and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+        if self.training:       # nn.BatchNorm2d bookkeeping (unused by the arithmetic: momentum is a constant); one launch
+            torch._foreach_add_([bn.num_batches_tracked for _, bn in self._layers() if bn.num_batches_tracked is not None], 1)
         return ops.ConvObjectsFunction.apply(img, self.training, eps, momentum, running, *params)
 
     def forward(self, img: torch.Tensor) -> torch.Tensor:
@@ -151,9 +151,8 @@ class RelationalLayer(RelationalLayerBase):
         if self.training and p > 0 and self.dropout_mask_override is not None:
             mask = self.dropout_mask_override.to(device=x_g.device, dtype=torch.uint8).contiguous()
         elif self.training and p > 0:
-            # draw the keep-mask with torch's own dropout so the RNG stream matches the reference's
-            ones = torch.ones(x_g.shape[0], self.f_fc2.out_features, device=x_g.device)
-            mask = (F.dropout(ones, p, True) != 0).to(torch.uint8)
+            # keep-mask ~ Bernoulli(1 - p) from torch's CUDA generator (philox: CUDA-graph safe), one launch
+            mask = torch.empty(x_g.shape[0], self.f_fc2.out_features, dtype=torch.uint8, device=x_g.device).bernoulli_(1.0 - p)
         return ops.FHeadFunction.apply(x_g, self.f_fc1.weight, self.f_fc1.bias, self.f_fc2.weight, self.f_fc2.bias,
                                        self.f_fc3.weight, self.f_fc3.bias, mask, 1.0 / (1.0 - p) if p < 1 else 0.0)
 

@@ -142,6 +142,26 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_tensor_device(fn):
+    """Run an autograd.Function forward / backward with the CUDA device of its first tensor argument current, so the
+    stream, the scratch buffers and the SM count all belong to the device the data lives on (a model moved with
+    ``.cuda(1)`` without ``torch.cuda.set_device(1)``, autograd worker threads)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(ctx, *args):
+        dev = next((a.device for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None:
+            saved = getattr(ctx, "saved_tensors", ())
+            dev = next((a.device for a in saved if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None:
+            return fn(ctx, *args)
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+
+    return wrapper
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
@@ -169,6 +189,7 @@ class RelationFunction(torch.autograd.Function):
     """
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, q, qinj, precision, *wb):
         _require_cuda(x, q, *wb)
         L = len(wb) // 2
@@ -201,6 +222,7 @@ class RelationFunction(torch.autograd.Function):
         return xg
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dxg):
         x_, q_, *ws = ctx.saved_tensors
         cfg, L = ctx.cfg, ctx.L
@@ -230,6 +252,7 @@ class FHeadFunction(torch.autograd.Function):
     ``drop_mask`` is a uint8 [B,F2] keep-mask drawn by the caller from torch's RNG (or None)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, xg, w1, b1, w2, b2, w3, b3, drop_mask, keep_scale):
         _require_cuda(xg, w1, b1, w2, b2, w3, b3, drop_mask)
         t = [_f32c(v) for v in (xg, w1, b1, w2, b2, w3, b3)]
@@ -251,6 +274,7 @@ class FHeadFunction(torch.autograd.Function):
         return logp
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dlogp):
         logp, saved, xg, w1, w2, w3, mask = ctx.saved_tensors
         cfg = ctx.cfg
@@ -279,6 +303,7 @@ class QuestionEncoderFunction(torch.autograd.Function):
     forward(tokens [B,T] int64, emb [V,E], w_ih [4H,E], w_hh [4H,H], b_ih [4H], b_hh [4H]) -> q [B,H]"""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, tokens, emb, w_ih, w_hh, b_ih, b_hh):
         _require_cuda(tokens, emb, w_ih, w_hh, b_ih, b_hh)
         if tokens.dtype != torch.int64:
@@ -305,6 +330,7 @@ class QuestionEncoderFunction(torch.autograd.Function):
         return q
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dq):
         tok, saved, *ps = ctx.saved_tensors
         dq_ = _f32c(dq)
@@ -334,6 +360,7 @@ class ConvObjectsFunction(torch.autograd.Function):
     params per layer: conv weight, conv bias, bn weight, bn bias."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, img, training, eps, momentum, running, *params):
         _require_cuda(img, *params, *running)
         img_ = _f32c(img)
@@ -365,6 +392,7 @@ class ConvObjectsFunction(torch.autograd.Function):
         return objects
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dobjects):
         img_, *ps = ctx.saved_tensors
         cfg = ctx.cfg
@@ -383,14 +411,18 @@ class ConvObjectsFunction(torch.autograd.Function):
 
 def clip_adam_(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
                lr: float, clip_norm: float = 50.0, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-               grad_scale: float = 1.0) -> torch.Tensor:
+               grad_scale: float = 1.0, step_dev: torch.Tensor = None, lr_dev: torch.Tensor = None,
+               total_out: torch.Tensor = None) -> torch.Tensor:
     """Fused clip_grad_norm + Adam(weight_decay) on flat fp32 buffers (reference train.py:45-48, 330).
-    Returns the (pre-clip) total gradient norm as a 1-element device tensor."""
-    _require_cuda(params, grads, exp_avg, exp_avg_sq)
+    Returns the (pre-clip) total gradient norm as a 1-element device tensor.  `step_dev` (int32[1]) / `lr_dev` (fp32[1]):
+    device-resident step counter (incremented by the call) and learning rate, for CUDA-graph replays."""
+    _require_cuda(params, grads, exp_avg, exp_avg_sq, step_dev, lr_dev)
     n = params.numel()
     cfg = AdamCfg(n, lr, betas[0], betas[1], eps, weight_decay, clip_norm if clip_norm else 0.0, grad_scale, step)
     norm_scratch = _scratch_bytes(params.device, "adam", 4 * 1032)
-    total = torch.empty(1, dtype=torch.float32, device=params.device)
+    total = total_out if total_out is not None else torch.empty(1, dtype=torch.float32, device=params.device)
     check(lib().rn_clip_adam(C.byref(cfg), params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(),
-                             exp_avg_sq.data_ptr(), norm_scratch.data_ptr(), total.data_ptr(), _stream()), "rn_clip_adam")
+                             exp_avg_sq.data_ptr(), norm_scratch.data_ptr(), total.data_ptr(),
+                             step_dev.data_ptr() if step_dev is not None else None,
+                             lr_dev.data_ptr() if lr_dev is not None else None, _stream()), "rn_clip_adam")
     return total

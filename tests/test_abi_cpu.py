@@ -29,7 +29,7 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.rn_abi_version() == 1
+    assert lib.rn_abi_version() == _lib.RN_ABI_VERSION == int(re.search(r"#define RN_ABI_VERSION (\d+)", header).group(1))
 
 
 def test_argument_validation_without_gpu(lib):
@@ -47,6 +47,10 @@ def test_argument_validation_without_gpu(lib):
     assert lib.rn_relation_workspace(C.byref(sd), C.byref(a), C.byref(b)) == -2
     cc = _lib.ConvCfg(4, 100, 1, 1e-5, 0.1)                      # side not a multiple of 16
     assert lib.rn_conv_workspace(C.byref(cc), C.byref(a), C.byref(b)) == -1
+    lc = _lib.LstmCfg(4, 20, 83, 32, 256, 1)                     # hidden size 256: no kernel, the host keeps nn.LSTM
+    assert lib.rn_lstm_supported(C.byref(lc)) == 0
+    assert lib.rn_lstm_workspace(C.byref(lc), C.byref(a), C.byref(b)) == -2
+    assert lib.rn_lstm_supported(C.byref(_lib.LstmCfg(4, 20, 83, 32, 128, 1))) == 1
     # NULL pointers are rejected before any CUDA call
     assert lib.rn_relation_fwd(C.byref(ok), None, None, None, None, None, None, None, None) == -1
 

@@ -116,17 +116,21 @@ def main(args):
     if args.resume:
         checkpoint = torch.load(args.resume, map_location="cpu", weights_only=True)
         checkpoint = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in checkpoint.items()}
-        model.load_state_dict(checkpoint, strict=False)
+        model.load_state_dict(checkpoint, strict=True)         # like the reference: a key mismatch is an error
         m = re.search(r'epoch_(\d+)', os.path.basename(args.resume))
         start_epoch = int(m.group(1)) + 1 if m else 1
         print('==> loaded checkpoint {} (next epoch {})'.format(args.resume, start_epoch))
     if args.conv_transfer_learn:
         checkpoint = torch.load(args.conv_transfer_learn, map_location="cpu", weights_only=True)
         conv = {k.split("conv.", 1)[1]: v for k, v in checkpoint.items() if "conv." in k}
-        model.conv.load_state_dict(conv, strict=False)
+        model.conv.load_state_dict(conv, strict=True)
         print('==> loaded conv layers from {}'.format(args.conv_transfer_learn))
 
+    if args.batch_size % world:
+        raise SystemExit('--batch-size {} is not divisible by the number of ranks {}'.format(args.batch_size, world))
     per_rank_bs = args.batch_size // world
+    # identical parameters on every rank (seeded above), but independent dropout masks per rank
+    torch.cuda.manual_seed(args.seed + rank)
     if args.test:
         test(synthetic_batches(args, hyp, args.synthetic_batches, per_rank_bs, device, args.seed + 1), model, start_epoch)
         return
@@ -134,9 +138,20 @@ def main(args):
     lr = args.lr * (args.lr_gamma ** ((start_epoch - 1) // args.lr_step))
     optimizer = FlatClipAdam(model.parameters(), lr=min(lr, args.lr_max), weight_decay=1e-4, clip_norm=args.clip_norm)
     print('Training ({} epochs) is starting...'.format(args.epochs))
+    bs = args.batch_size
     for epoch in range(start_epoch, args.epochs + 1):
-        if (epoch - 1) % args.lr_step == 0 and epoch > 1 and optimizer.lr * args.lr_gamma <= args.lr_max:
-            optimizer.lr *= args.lr_gamma                     # the LR *increases* until lr_max (train.py:330-350)
+        # batch-size schedule of the reference (train.py:337-341): grows by bs_gamma every bs_step epochs up to bs_max
+        if ((args.bs_max > 0 and bs < args.bs_max) or args.bs_max < 0) and (epoch % args.bs_step == 0 or epoch == start_epoch):
+            bs = int(args.batch_size * (args.bs_gamma ** (epoch // args.bs_step)))
+            if args.bs_max > 0:
+                bs = min(bs, args.bs_max)
+            bs -= bs % world
+            per_rank_bs = bs // world
+            print('Dataset reinitialized with batch size {}'.format(bs))
+        # StepLR-like schedule: the LR is multiplied by lr_gamma every lr_step epochs WHILE it is below lr_max
+        # (train.py:332-333, 350-351: the reference steps its scheduler only while get_lr() < lr_max)
+        if (epoch - 1) % args.lr_step == 0 and epoch > 1 and (args.lr_max < 0 or optimizer.lr < args.lr_max):
+            optimizer.set_lr(optimizer.lr * args.lr_gamma)
         print('Current learning rate: {}'.format(optimizer.lr))
         train(synthetic_batches(args, hyp, args.synthetic_batches, per_rank_bs, device, args.seed + 100 * epoch + rank),
               args.synthetic_batches, model, optimizer, epoch, args)
