@@ -106,6 +106,15 @@ int rn_relation_bwd(const rn_relation_cfg* cfg, const float* dxg, const float* x
                     const float* const* h_g_w, const void* saved, float* dx, float* dq,
                     float* const* h_dg_w, float* const* h_dg_b, void* scratch, void* stream);
 
+/* ---- feature extraction (extract.py:63-74) ---- */
+/* maxf / avgf [B, W]: max and mean over the P rows of each sample of z / max(||z||_2, 1e-12), z [B * P, ld] fp32 using the
+ * first W columns (W <= 512).  scratch: floats, B * 32 * 2 * W. */
+int rn_extract_stats(const float* z, int B, long long P, int ld, int W, float* maxf, float* avgf, float* scratch,
+                     void* stream);
+/* *out = device pointer of H_{l+1} = relu(g layer l) [B * n * n, G] inside the `saved` buffer of an RN_PRECISION_FP32
+ * training-mode rn_relation_fwd: the tensor a forward hook on rl.g_layers[l + 1] receives as its input (extract.py:43-47). */
+int rn_relation_activation(const rn_relation_cfg* cfg, const void* saved, int l, const float** out);
+
 /* ---- f-MLP head: fc1 -> ReLU -> fc2 -> Dropout -> ReLU -> fc3 -> log_softmax (model.py:155-162) ---- */
 typedef struct rn_f_cfg {
   int32_t B;        /* samples */
@@ -139,6 +148,8 @@ typedef struct rn_conv_cfg {
   int32_t training;  /* 1: batch statistics (+ running-stat update), 0: running statistics */
   float eps;         /* BatchNorm eps (1e-5) */
   float momentum;    /* BatchNorm momentum (0.1) */
+  int32_t img_u8;    /* 1: `img` is uint8 [B,3,S,S] (raw pixels); the first layer computes x = u / 255 (torchvision ToTensor,
+                      * train.py:182-188) while staging -- a quarter of the host-to-device bytes.  0: fp32 in [0,1] */
 } rn_conv_cfg;
 
 /* Per-layer parameter block, host array of RN_CONV_LAYERS entries (device pointers inside). */
@@ -155,7 +166,7 @@ typedef struct rn_conv_layer {
  * objects out: [B, d*d, 26] with d = side/16 -- channels 0..23 the layer-4 activations, 24/25 the
  * x/y coordinates linspace(-d/2, d/2, d) (model.py:208-213). */
 int rn_conv_workspace(const rn_conv_cfg* cfg, size_t* saved_floats, size_t* scratch_floats);
-int rn_conv_fwd(const rn_conv_cfg* cfg, const float* img, const rn_conv_layer* h_layers, float* objects,
+int rn_conv_fwd(const rn_conv_cfg* cfg, const void* img, const rn_conv_layer* h_layers, float* objects,
                 float* saved, float* scratch, void* stream);
 
 typedef struct rn_conv_grads {
@@ -167,7 +178,7 @@ typedef struct rn_conv_grads {
 
 /* dobjects [B, d*d, 26] in (coordinate columns ignored).  Gradients overwritten.  No image gradient
  * (utils.py:135,143: images never require grad). */
-int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float* dobjects, const rn_conv_layer* h_layers,
+int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img, const float* dobjects, const rn_conv_layer* h_layers,
                 const float* saved, const rn_conv_grads* h_grads, float* scratch, void* stream);
 
 /* ---- question encoder: Embedding -> 1-layer LSTM (zero initial state) -> last hidden state (model.py:39-58) ---- */

@@ -31,7 +31,7 @@ class FCfg(C.Structure):
 
 class ConvCfg(C.Structure):
     _fields_ = [("B", C.c_int32), ("side", C.c_int32), ("training", C.c_int32), ("eps", C.c_float),
-                ("momentum", C.c_float)]
+                ("momentum", C.c_float), ("img_u8", C.c_int32)]
 
 
 class ConvLayer(C.Structure):
@@ -63,6 +63,8 @@ SIGNATURES = {
     "rn_relation_fwd": (C.c_int, [C.POINTER(RelationCfg), _P, _P, C.POINTER(_P), C.POINTER(_P), _P, _P, _P, _P]),
     "rn_relation_bwd": (C.c_int, [C.POINTER(RelationCfg), _P, _P, _P, C.POINTER(_P), _P, _P, _P, C.POINTER(_P),
                                   C.POINTER(_P), _P, _P]),
+    "rn_extract_stats": (C.c_int, [_P, C.c_int, C.c_longlong, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "rn_relation_activation": (C.c_int, [C.POINTER(RelationCfg), _P, C.c_int, C.POINTER(_P)]),
     "rn_f_fwd": (C.c_int, [C.POINTER(FCfg)] + [_P] * 11),
     "rn_f_bwd": (C.c_int, [C.POINTER(FCfg)] + [_P] * 17),
     "rn_conv_workspace": (C.c_int, [C.POINTER(ConvCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

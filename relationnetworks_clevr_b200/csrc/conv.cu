@@ -118,6 +118,35 @@ __device__ __forceinline__ void stage_patch_finish(float (*patch)[kPatch][kPW], 
   }
 }
 
+// uint8 images ([B,3,S,S] bytes, the pixels torchvision's ToTensor divides by 255): converted while staging, so the host
+// copies a quarter of the bytes.  x = u / 255 with a true division -- bit-identical to ToTensor's float().div(255).
+template <int CC>
+__device__ __forceinline__ void stage_patch_u8(float (*patch)[kPatch][kPW], const unsigned char* __restrict__ inb, int ih0,
+                                               int iw0, int hin, int tid) {
+  if ((hin & 3) == 0) {
+    for (int idx = tid; idx < CC * kPatch * kPV; idx += 256) {
+      const int ci = idx / (kPatch * kPV), rem = idx - ci * (kPatch * kPV);
+      const int r = rem / kPV, v = rem - r * kPV;
+      const int ih = ih0 + r, iw = iw0 - kPO + 4 * v;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((unsigned)ih < (unsigned)hin && (unsigned)iw < (unsigned)hin) {
+        const uchar4 u = *reinterpret_cast<const uchar4*>(inb + ((size_t)ci * hin + ih) * hin + iw);
+        t = make_float4(__fdiv_rn((float)u.x, 255.f), __fdiv_rn((float)u.y, 255.f), __fdiv_rn((float)u.z, 255.f),
+                        __fdiv_rn((float)u.w, 255.f));
+      }
+      *reinterpret_cast<float4*>(&patch[ci][r][4 * v]) = t;
+    }
+  } else {
+    for (int idx = tid; idx < CC * kPatch * kPatch; idx += 256) {
+      const int ci = idx / (kPatch * kPatch), rem = idx % (kPatch * kPatch);
+      const int r = rem / kPatch, c = rem % kPatch;
+      const int ih = ih0 + r, iw = iw0 + c;
+      const bool valid = ih >= 0 && ih < hin && iw >= 0 && iw < hin;
+      patch[ci][r][c + kPO] = valid ? __fdiv_rn((float)inb[((size_t)ci * hin + ih) * hin + iw], 255.f) : 0.f;
+    }
+  }
+}
+
 template <int CC>
 __device__ __forceinline__ void stage_patch(float (*patch)[kPatch][kPW], const float* __restrict__ inb,
                                             const float* __restrict__ in_aff, int ci0, int ih0, int iw0, int hin,
@@ -132,7 +161,7 @@ __device__ __forceinline__ void stage_patch(float (*patch)[kPatch][kPW], const f
 // 24 accumulators per thread; per input channel 25 input LDS + 18 broadcast weight LDS.128 feed 216 FFMA.
 // Warp = 8 quads (x) x 4 channel groups: input reads hit 8 distinct banks and broadcast over the groups.
 // ------------------------------------------------------------------------------------------
-template <int CIN>
+template <int CIN, bool U8 = false>
 __global__ void __launch_bounds__(256)
 conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ w,
                 const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ stat_part, int hin,
@@ -151,7 +180,8 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, 
   const int b = blockIdx.y;
   const int oh0 = (blockIdx.x / tiles_x) * kTile, ow0 = (blockIdx.x % tiles_x) * kTile;
   const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
-  const float* inb = in + (size_t)b * CIN * hin * hin;
+  const float* inb = U8 ? in : in + (size_t)b * CIN * hin * hin;
+  const unsigned char* inb8 = reinterpret_cast<const unsigned char*>(in) + (size_t)b * CIN * hin * hin;
 
   // packed fp32x2 accumulators (FFMA2: two FMAs per issue slot on sm_100): acc[pixel][channel pair]
   float2 acc[4][3];
@@ -162,7 +192,8 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, 
 
   auto issue = [&](int k) {
     const int buf = k % NBUF, ci0 = k * CC;
-    stage_patch_issue<CC>(patch[buf], inb, ci0, ih0, iw0, hin, tid);
+    if (U8) stage_patch_u8<CC>(patch[buf], inb8, ih0, iw0, hin, tid);
+    else stage_patch_issue<CC>(patch[buf], inb, ci0, ih0, iw0, hin, tid);
     for (int idx = tid; idx < CC * kC * 9; idx += 256) {
       const int ci = idx / (kC * 9), rem = idx % (kC * 9);
       const int co = rem / 9, t = rem % 9;
@@ -173,7 +204,8 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, 
   issue(0);
   for (int k = 0; k < NCHUNK; ++k) {
     const int buf = k % NBUF;
-    stage_patch_finish<CC>(patch[buf], in_aff, k * CC, ih0, iw0, hin, tid);
+    if (U8) cp_async_wait_all();      // (the weights)
+    else stage_patch_finish<CC>(patch[buf], in_aff, k * CC, ih0, iw0, hin, tid);
     __syncthreads();              // chunk k is complete; everyone is done reading the other buffer
     if (k + 1 < NCHUNK) issue(k + 1);
     if (oh0 + 2 * qy >= hout) continue;      // this warp's quad row is outside the image (small layers): staging only
@@ -459,7 +491,7 @@ static size_t wgrad_smem_bytes() {
              : ((size_t)wgrad_chunk<CIN>() * kPatch * kPW + (size_t)kC * kDyLd) * sizeof(float);
 }
 
-template <int CIN>
+template <int CIN, bool U8 = false>
 __global__ void __launch_bounds__(256)
 conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ yout,
                   const float* __restrict__ dA, const float* __restrict__ aff_out, const float* __restrict__ coef,
@@ -481,7 +513,8 @@ conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff
   const int b = blockIdx.y;
   const int oh0 = (blockIdx.x / tiles_x) * kTile, ow0 = (blockIdx.x % tiles_x) * kTile;
   const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
-  const float* inb = in + (size_t)b * CIN * hin * hin;
+  const float* inb = U8 ? in : in + (size_t)b * CIN * hin * hin;
+  const unsigned char* inb8 = reinterpret_cast<const unsigned char*>(in) + (size_t)b * CIN * hin * hin;
   float* out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kC * CIN * 9);
 
   stage_dy<kTile, kTile, kTile, kDyLd>(dys, yout + (size_t)b * kC * hout * hout, dA + (size_t)b * kC * hout * hout, aff_out,
@@ -489,7 +522,8 @@ conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ in_aff
 
   for (int ci0 = 0; ci0 < CIN; ci0 += CC) {
     __syncthreads();
-    stage_patch<CC>(patch, inb, in_aff, ci0, ih0, iw0, hin, tid);
+    if (U8) stage_patch_u8<CC>(patch, inb8, ih0, iw0, hin, tid);
+    else stage_patch<CC>(patch, inb, in_aff, ci0, ih0, iw0, hin, tid);
     __syncthreads();
     float2 acc2[3][9];           // packed (channel 2j, 2j+1) accumulators: FFMA2
 #pragma unroll
@@ -706,8 +740,9 @@ extern "C" int rn_conv_workspace(const rn_conv_cfg* cfg, size_t* saved_floats, s
   return RN_OK;
 }
 
-extern "C" int rn_conv_fwd(const rn_conv_cfg* cfg, const float* img, const rn_conv_layer* L, float* objects,
+extern "C" int rn_conv_fwd(const rn_conv_cfg* cfg, const void* img_any, const rn_conv_layer* L, float* objects,
                            float* saved, float* scratch, void* stream) {
+  const float* img = static_cast<const float*>(img_any);
   RN_TRY(validate_conv(cfg));
   RN_CHECK_ARG(img && L && objects && saved && scratch, "NULL pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -722,7 +757,9 @@ extern "C" int rn_conv_fwd(const rn_conv_cfg* cfg, const float* img, const rn_co
     const int hin = p.h[l], hout = p.h[l + 1], tx = cdiv(hout, kTile);
     dim3 grid(p.tiles[l], cfg->B);
     float* part = cfg->training ? scratch : nullptr;
-    if (l == 0)
+    if (l == 0 && cfg->img_u8)
+      conv_fwd_kernel<3, true><<<grid, 256, 0, st>>>(in, in_aff, L[l].w, L[l].bias, y, part, hin, hout, tx);
+    else if (l == 0)
       conv_fwd_kernel<3><<<grid, 256, 0, st>>>(in, in_aff, L[l].w, L[l].bias, y, part, hin, hout, tx);
     else
       conv_fwd_kernel<kC><<<grid, 256, 0, st>>>(in, in_aff, L[l].w, L[l].bias, y, part, hin, hout, tx);
@@ -741,8 +778,9 @@ extern "C" int rn_conv_fwd(const rn_conv_cfg* cfg, const float* img, const rn_co
   return RN_OK;
 }
 
-extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float* dobjects, const rn_conv_layer* L,
+extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const float* dobjects, const rn_conv_layer* L,
                            const float* saved, const rn_conv_grads* Gr, float* scratch, void* stream) {
+  const float* img = static_cast<const float*>(img_any);
   RN_TRY(validate_conv(cfg));
   RN_CHECK_ARG(img && dobjects && L && saved && Gr && scratch, "NULL pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -780,7 +818,11 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const float* img, const float
     const float* in_aff = l == 0 ? nullptr : saved + p.aff_off[l - 1];
     dim3 grid(p.tiles[l], cfg->B);
     const int cin = l == 0 ? 3 : kC;
-    if (l == 0) {
+    if (l == 0 && cfg->img_u8) {
+      const size_t smem = wgrad_smem_bytes<3>();
+      RN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv_wgrad_kernel<3, true><<<grid, 256, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, hin, hout, tx);
+    } else if (l == 0) {
       const size_t smem = wgrad_smem_bytes<3>();
       RN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       conv_wgrad_kernel<3><<<grid, 256, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, hin, hout, tx);

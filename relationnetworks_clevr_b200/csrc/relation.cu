@@ -526,3 +526,93 @@ extern "C" int rn_relation_bwd(const rn_relation_cfg* cfg, const float* dxg, con
   if (!tc_supported(s)) return fail(RN_ERR_UNSUPPORTED, "tcgen05 path does not support this shape");
   return tc_relation_bwd(s, cfg->precision, dxg, x, q, h_g_w, saved, dx, dq, h_dg_w, h_dg_b, scratch, st);
 }
+
+// ------------------------------------------------------------------------------------------
+// feature extraction support (reference extract.py:63-74): per sample, the max and the mean over all pair rows of the
+// L2-normalised input of a g layer.  z [B * P, ld] fp32, the first `W` columns are used (the hook strips the question
+// columns when the layer is the question-injection layer).  Two launches, fixed-order reductions.
+// ------------------------------------------------------------------------------------------
+namespace rn {
+constexpr int kExChunks = 32, kExMaxPerLane = 16;      // W <= 512
+
+__global__ void __launch_bounds__(256)
+extract_partial_kernel(const float* __restrict__ z, long long P, int ld, int W, float* __restrict__ part) {
+  __shared__ float smax[8][512], ssum[8][512];
+  const int b = blockIdx.x, chunk = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long per = (P + kExChunks - 1) / kExChunks;
+  const long long r0 = chunk * per, r1 = min(P, r0 + per);
+  float vmax[kExMaxPerLane], vsum[kExMaxPerLane];
+#pragma unroll
+  for (int k = 0; k < kExMaxPerLane; ++k) { vmax[k] = -INFINITY; vsum[k] = 0.f; }
+  for (long long r = r0 + warp; r < r1; r += 8) {
+    const float* row = z + ((long long)b * P + r) * ld;
+    float v[kExMaxPerLane], ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kExMaxPerLane; ++k) {
+      const int j = lane + 32 * k;
+      v[k] = j < W ? row[j] : 0.f;
+      ss = fmaf(v[k], v[k], ss);
+    }
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);        // F.normalize(p=2, eps=1e-12)
+#pragma unroll
+    for (int k = 0; k < kExMaxPerLane; ++k) {
+      const float x = v[k] * inv;
+      vmax[k] = fmaxf(vmax[k], x);
+      vsum[k] += x;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kExMaxPerLane; ++k) { smax[warp][lane + 32 * k] = vmax[k]; ssum[warp][lane + 32 * k] = vsum[k]; }
+  __syncthreads();
+  for (int j = threadIdx.x; j < W; j += 256) {
+    float m = smax[0][j], s = ssum[0][j];
+#pragma unroll
+    for (int wv = 1; wv < 8; ++wv) { m = fmaxf(m, smax[wv][j]); s += ssum[wv][j]; }
+    float* o = part + (((size_t)b * kExChunks + chunk) * 2) * W;
+    o[j] = m;
+    o[W + j] = s;
+  }
+}
+
+__global__ void extract_final_kernel(const float* __restrict__ part, long long P, int W, float* __restrict__ maxf,
+                                     float* __restrict__ avgf) {
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
+    float m = -INFINITY, s = 0.f;
+    for (int c = 0; c < kExChunks; ++c) {
+      const float* o = part + (((size_t)b * kExChunks + c) * 2) * W;
+      m = fmaxf(m, o[j]);
+      s += o[W + j];
+    }
+    maxf[(size_t)b * W + j] = m;
+    avgf[(size_t)b * W + j] = s / (float)P;
+  }
+}
+}  // namespace rn
+
+extern "C" int rn_extract_stats(const float* z, int B, long long P, int ld, int W, float* maxf, float* avgf, float* scratch,
+                                void* stream) {
+  RN_CHECK_ARG(z && maxf && avgf && scratch, "NULL pointer argument");
+  RN_CHECK_ARG(B > 0 && B <= 65535 && P > 0 && W > 0 && W <= ld && W <= 32 * rn::kExMaxPerLane, "bad shape (B=%d P=%lld ld=%d W=%d)", B,
+               P, ld, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rn::extract_partial_kernel<<<dim3(B, rn::kExChunks), 256, 0, st>>>(z, P, ld, W, scratch);
+  RN_LAUNCH_CHECK("extract_partial_kernel");
+  rn::extract_final_kernel<<<B, 256, 0, st>>>(scratch, P, W, maxf, avgf);
+  RN_LAUNCH_CHECK("extract_final_kernel");
+  return RN_OK;
+}
+
+// Device pointer of the materialised activation H_{l+1} = relu(layer l) [B * n * n, G] inside the `saved` buffer of an
+// RN_PRECISION_FP32 training-mode forward (l in [0, L)): what a forward hook on g layer l + 1 receives as its input.
+extern "C" int rn_relation_activation(const rn_relation_cfg* cfg, const void* saved, int l, const float** out) {
+  RN_TRY(validate_cfg(cfg));
+  RN_CHECK_ARG(saved && out, "NULL pointer argument");
+  RN_CHECK_ARG(cfg->precision == RN_PRECISION_FP32 && cfg->training != 0, "activations are materialised by the fp32 training-mode forward only");
+  RN_CHECK_ARG(l >= 0 && l < cfg->L, "l must be in [0, L) (l=%d)", l);
+  RelShape s(*cfg);
+  SimtSaved sv = simt_carve_saved(s, const_cast<void*>(saved), s.L);
+  *out = sv.H[l];
+  return RN_OK;
+}

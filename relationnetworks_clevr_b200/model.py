@@ -54,6 +54,7 @@ class ConvInputModel(nn.Module):
 
     def forward(self, img: torch.Tensor) -> torch.Tensor:
         obj = self.objects(img)                       # [B, d*d, 26]
+        self.last_objects = obj                       # RN.forward reuses it when it goes through this module (hooks on `conv`)
         b, n, _ = obj.shape
         d = int(round(n ** 0.5))
         return obj[:, :, :24].permute(0, 2, 1).reshape(b, 24, d, d)
@@ -142,10 +143,55 @@ class RelationalLayer(RelationalLayerBase):
         b, n, k = x.shape
         return ops.RelationFunction.apply(x, qst, self.quest_inject_position, self._resolve_precision(n, k), *wb)
 
+    def _hooked(self) -> bool:
+        return any(len(layer._forward_hooks) or len(layer._forward_pre_hooks) for layer in self.g_layers)
+
+    def _forward_materialised(self, x: torch.Tensor, qst: torch.Tensor) -> torch.Tensor:
+        """Feature-extraction path (reference extract.py:40-47 hooks ``rl.g_layers[i]``): the fp32 kernels keep every
+        g-layer activation in device memory and each hooked layer's hooks are called with the tensor the reference's
+        nn.Linear would have received -- [B*n*n, fan_in] including the question columns at the injection layer.  The
+        hook's `output` argument is the layer's post-ReLU activation (the pre-activation is never stored)."""
+        wb = []
+        for layer in self.g_layers:
+            wb += [layer.weight, layer.bias]
+        x_g, acts = ops.relation_forward_materialised(x, qst, self.quest_inject_position, *wb)
+        b, n, k = x.shape
+        for idx, layer in enumerate(self.g_layers):
+            if not (len(layer._forward_hooks) or len(layer._forward_pre_hooks)):
+                continue
+            if idx == 0:      # the literal pair matrix (model.py:112-127): row a*n + c = [x_c | x_a]
+                inp = torch.cat([x.unsqueeze(1).expand(b, n, n, k), x.unsqueeze(2).expand(b, n, n, k)], 3).reshape(b * n * n, 2 * k)
+            else:
+                inp = acts[idx - 1]
+            if idx == self.quest_inject_position:
+                inp = torch.cat([inp, qst.unsqueeze(1).expand(b, n * n, qst.shape[1]).reshape(b * n * n, -1)], 1)
+            for hook in layer._forward_pre_hooks.values():
+                hook(layer, (inp,))
+            for hook in layer._forward_hooks.values():
+                hook(layer, (inp,), acts[idx])
+        return x_g
+
+    def extract(self, x: torch.Tensor, qst: torch.Tensor, layer_idx: int):
+        """(maxf, avgf) [B, width]: the aggregation of reference extract.py:63-74 for the input of g layer `layer_idx` --
+        per sample the max and the mean over all pair rows of the L2-normalised rows (question columns stripped at the
+        injection layer) -- computed by one reduction kernel over the materialised activation."""
+        got = {}
+        handle = self.g_layers[layer_idx].register_forward_hook(lambda m, i, o: got.__setitem__("z", i[0]))
+        try:
+            self._forward_materialised(x, qst)
+        finally:
+            handle.remove()
+        z = got["z"]
+        width = z.shape[1] - (self.qst_size if layer_idx == self.quest_inject_position else 0)
+        return ops.extract_stats(z, x.shape[0], width)
+
     def forward(self, x: torch.Tensor, qst: torch.Tensor):
-        x_g = self.relation(x, qst)
-        if self.extraction:
-            return None
+        if self.extraction or self._hooked():
+            x_g = self._forward_materialised(x, qst)
+            if self.extraction:
+                return None              # like the reference (model.py:147-148): extraction stops after g
+        else:
+            x_g = self.relation(x, qst)
         p = self.dropout.p
         mask = None
         if self.training and p > 0 and self.dropout_mask_override is not None:
@@ -184,7 +230,7 @@ class RN(nn.Module):
         if self.state_desc or os.environ.get("RN_B200_TEXT_STREAM", "1") == "0" or (self.text.use_kernel and self.text.hidden == 128):
             # (the question-encoder kernel is one short launch: nothing to gain from a side stream, and the step stays
             # a single-stream sequence that CUDA-graph capture takes as is)
-            x = img if self.state_desc else self.conv.objects(img)
+            x = img if self.state_desc else self._objects(img)
             qst = self.text(qst_idxs)
             return self.rl(x, qst)
         # The question encoder (PyTorch/cuDNN, a chain of small latency-bound kernels) runs on a side stream next to
@@ -194,10 +240,16 @@ class RN(nn.Module):
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             qst = self.text(qst_idxs)
-        x = self.conv.objects(img)
+        x = self._objects(img)
         cur.wait_stream(side)
         qst.record_stream(cur)
         return self.rl(x, qst)
+
+    def _objects(self, img: torch.Tensor) -> torch.Tensor:
+        if len(self.conv._forward_hooks) or len(self.conv._forward_pre_hooks):
+            self.conv(img)                    # through the module: hooks on `conv` see the [B,24,d,d] feature map (extract.py:47)
+            return self.conv.last_objects
+        return self.conv.objects(img)
 
     def build_coord_tensor(self, b, d):
         """Reference-compatible helper (model.py:208-218); the kernels do not use it."""

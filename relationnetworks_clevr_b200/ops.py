@@ -246,6 +246,51 @@ class RelationFunction(torch.autograd.Function):
         return (dx, dq, None, None, *grads)
 
 
+def relation_forward_materialised(x, q, qinj, *wb):
+    """Eval-time forward of the relation op on the fp32 kernels that KEEPS every g-layer activation in device memory:
+    returns (x_g [B,G], [H_1 .. H_L]) with H_{l+1} = relu(g layer l) as [B*n*n, G] views of one buffer.  This is what
+    forward hooks on ``rl.g_layers[i]`` (reference extract.py:43-47) need to see; the training / inference paths never
+    materialise these tensors (2.7 GB each at B = 640)."""
+    _require_cuda(x, q, *wb)
+    with torch.no_grad(), torch.cuda.device(x.device):
+        ws = [_f32c(t) for t in wb[0::2]]
+        bs = [_f32c(t) for t in wb[1::2]]
+        x_, q_ = _f32c(x), _f32c(q)
+        B, n, k = x_.shape
+        Q, G, L = q_.shape[1], ws[0].shape[0], len(ws)
+        cfg = relation_cfg(B, n, k, Q, G, L, qinj, "fp32", True)
+        sb, cb = C.c_size_t(), C.c_size_t()
+        check(lib().rn_relation_workspace(C.byref(cfg), C.byref(sb), C.byref(cb)), "rn_relation_workspace")
+        saved = torch.empty(max(sb.value, 256), dtype=torch.uint8, device=x.device)
+        scratch = _scratch_bytes(x.device, "relation", cb.value)
+        xg = torch.empty(B, G, dtype=torch.float32, device=x.device)
+        check(lib().rn_relation_fwd(C.byref(cfg), x_.data_ptr(), q_.data_ptr(), ptr_array(ws), ptr_array(bs), xg.data_ptr(),
+                                    saved.data_ptr(), scratch.data_ptr(), _stream()), "rn_relation_fwd")
+        acts = []
+        base = saved.data_ptr()
+        for l in range(L):
+            ptr = C.c_void_p()
+            check(lib().rn_relation_activation(C.byref(cfg), base, l, C.byref(ptr)), "rn_relation_activation")
+            off = ptr.value - base
+            acts.append(saved[off: off + B * n * n * G * 4].view(torch.float32).view(B * n * n, G))
+        return xg, acts
+
+
+def extract_stats(z: torch.Tensor, B: int, width: int):
+    """(max, mean) over the rows of each sample of the L2-normalised rows of z [B*P, ld], first `width` columns
+    (the aggregation of reference extract.py:63-74), one pass over z."""
+    _require_cuda(z)
+    z = _f32c(z)
+    P = z.shape[0] // B
+    with torch.cuda.device(z.device):
+        maxf = torch.empty(B, width, dtype=torch.float32, device=z.device)
+        avgf = torch.empty(B, width, dtype=torch.float32, device=z.device)
+        scratch = _scratch_bytes(z.device, "extract", 4 * B * 32 * 2 * width)
+        check(lib().rn_extract_stats(z.data_ptr(), B, P, z.shape[1], width, maxf.data_ptr(), avgf.data_ptr(), scratch.data_ptr(),
+                                     _stream()), "rn_extract_stats")
+    return maxf, avgf
+
+
 class FHeadFunction(torch.autograd.Function):
     """log_softmax(fc3(relu(dropout(fc2(relu(fc1(x_g)))))))  (reference model.py:155-162).
 
@@ -363,7 +408,8 @@ class ConvObjectsFunction(torch.autograd.Function):
     @_on_tensor_device
     def forward(ctx, img, training, eps, momentum, running, *params):
         _require_cuda(img, *params, *running)
-        img_ = _f32c(img)
+        img_u8 = img.dtype == torch.uint8        # raw pixels: converted (u / 255) inside the first conv layer's staging
+        img_ = img.detach().contiguous() if img_u8 else _f32c(img)
         ps = [_f32c(p) for p in params]
         for r in running:
             if r.dtype != torch.float32 or not r.is_contiguous():
@@ -371,7 +417,7 @@ class ConvObjectsFunction(torch.autograd.Function):
         B, cin, side, side2 = img_.shape
         if cin != 3 or side != side2:
             raise RuntimeError(f"expected [B,3,S,S] images, got {tuple(img_.shape)}")
-        cfg = ConvCfg(B, side, int(training), float(eps), float(momentum))
+        cfg = ConvCfg(B, side, int(training), float(eps), float(momentum), int(img_u8))
         sf, cf = C.c_size_t(), C.c_size_t()
         check(lib().rn_conv_workspace(C.byref(cfg), C.byref(sf), C.byref(cf)), "rn_conv_workspace")
         saved = torch.empty(sf.value, dtype=torch.float32, device=img.device)

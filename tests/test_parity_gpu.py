@@ -327,6 +327,27 @@ def test_conv_objects_match_oracle(B, side, training):
         assert f2.shape == (B, 24, d, d)
 
 
+@pytest.mark.parametrize("side", [64, 128])
+def test_conv_uint8_images_equal_totensor_path(side):
+    """Raw uint8 pixels fed straight to the first conv layer (converted u / 255 while staging) give bit-identical objects and
+    gradients to the reference's input pipeline, ToTensor() = float().div(255) on the host (train.py:182-188)."""
+    B = 3
+    p = _conv_params(side)
+    img_u8 = torch.randint(0, 256, (B, 3, side, side), dtype=torch.uint8, generator=torch.Generator().manual_seed(side))
+    d = side // 16
+    dobj = torch.randn(B, d * d, 26, generator=torch.Generator().manual_seed(2)).to(DEV)
+    res = []
+    for img in (img_u8.float().div(255).to(DEV), img_u8.to(DEV)):
+        m = R.ConvInputModel()
+        m.load_state_dict({k_[len("conv."):]: v for k_, v in p.items()}, strict=False)
+        m.to(DEV).train()
+        obj = m.objects(img)
+        obj.backward(dobj)
+        res.append([obj.detach()] + [prm.grad for prm in m.parameters()])
+    for a, b_ in zip(*res):
+        assert torch.equal(a, b_)
+
+
 def test_clip_adam_matches_oracle():
     gen = torch.Generator().manual_seed(9)
     n = 100_003
