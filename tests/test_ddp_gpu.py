@@ -27,7 +27,7 @@ def _model(dev):
     m.load_state_dict(O.seeded_params(hyp, 82, 28, seed=9), strict=False)
     m.to(dev).train()
     m.rl.precision = "fp32"                      # exact arithmetic: the test is about the exchange step
-    m.rl.dropout_mask_override = torch.ones(B // 2, hyp["f_fc2"], dtype=torch.uint8)
+    m.rl.dropout_mask_override = torch.ones(B // 2, hyp["f_fc2"], dtype=torch.uint8, device=dev)      # (on the device: capturable)
     return m
 
 
@@ -54,6 +54,10 @@ def _worker(rank, world, init_file, out_file, graph):
     torch.cuda.synchronize()
     assert opt.step_count == 1
     torch.save(opt.flat.cpu(), f"{out_file}.{rank}")
+    if graph:
+        del g                  # the captured graph holds NCCL work: release it before the communicator goes away
+    dist.barrier()
+    torch.cuda.synchronize()
     dist.destroy_process_group()
 
 
