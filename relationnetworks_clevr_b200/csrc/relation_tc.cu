@@ -1054,7 +1054,7 @@ __global__ void __launch_bounds__(k3Threads, 1) rn_g_fwd3_kernel(const ChainPara
   } else if (warp >= 12) {
     // ================= operand generator: 8 warps, thread = (row, column half) =================
     // register pool of the CTA = 640 x 96 at launch: 128 x 48 (control) + 256 x 88 (generator) + 256 x 128 (epilogue) = 61440
-    reg_dec<88>();
+    // (generator keeps the 96 registers of the launch)
     const int q = warp & 3, ch = (warp - 12) >> 2, gt = threadIdx.x - 384;
     const int row = q * 32 + lane;
     uint32_t swz[8];
@@ -1072,63 +1072,65 @@ __global__ void __launch_bounds__(k3Threads, 1) rn_g_fwd3_kernel(const ChainPara
       const uint32_t buf = (3u * (uint32_t)i) & 1u;
       const float4* up = reinterpret_cast<const float4*>(p.U4) + ((size_t)b * (kG / 4) + ch * 32) * p.n + c;      // + g4 * n
       const float4* vp = reinterpret_cast<const float4*>(p.Vb + ((size_t)b * p.n + a) * kG + ch * 128);
-      float4 u[4], v[4];
+      // U is streamed through a 3-deep register ring of 16-column blocks (two blocks = 128 bytes per thread in flight:
+      // the L2 round trip, not issue slots, paces this warp role); V' rows are warp-uniform L1 hits, loaded at use.
+      float4 u[3][4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {                      // first 16 columns: in flight while waiting for the buffer
-        u[g] = __ldg(up + (size_t)g * p.n);
-        v[g] = __ldg(vp + g);
-      }
+      for (int pb = 0; pb < 2; ++pb)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) u[pb][g] = __ldg(up + (size_t)(pb * 4 + g) * p.n);
       if (i > 0) {
         mbar_wait(smem_u32(&bars->gen_go), go_phase);
         go_phase ^= 1;
         tc_fence_after_sync();
       }
       PROF3_ACC(0);
-      char* a_dst = smem + buf * kATile;
+      char* a_dst = smem + buf * kATile + (row >> 3) * 1024 + (row & 7) * 128;
+      const int r7 = row & 7;
       const uint32_t alo = tmem_base + ((uint32_t)(q * 32) << 16) + k3AloCol + buf * 128 + ch * 64;
       uint32_t* mrow = p.masks + ((size_t)tile * kTileM + row) * 8 + ch * 4;       // masks[0] = M1, same layout as M2..M4
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {                    // 32 columns = 16 tensor-memory columns per store
-        uint32_t lo[16];
-        uint32_t bits = 0;
+      uint32_t lo[16];
+      uint32_t bits = 0;
 #pragma unroll
-        for (int h16 = 0; h16 < 2; ++h16) {
+      for (int blk = 0; blk < 8; ++blk) {                 // 16 columns per block
+        if (blk + 2 < 8) {
 #pragma unroll
-          for (int g8 = 0; g8 < 2; ++g8) {
-            const float4 u0 = u[2 * g8], u1 = u[2 * g8 + 1], v0 = v[2 * g8], v1 = v[2 * g8 + 1];
-            uint4 o;
-            uint32_t* l4 = lo + h16 * 8 + g8 * 4;
-            split_relu_half2(u0.x + v0.x, u0.y + v0.y, o.x, l4[0]);
-            split_relu_half2(u0.z + v0.z, u0.w + v0.w, o.y, l4[1]);
-            split_relu_half2(u1.x + v1.x, u1.y + v1.y, o.z, l4[2]);
-            split_relu_half2(u1.z + v1.z, u1.w + v1.w, o.w, l4[3]);
-            if (SAVE) {
-              bits |= half2_pos_mask(o.x) & mask_pair_const(h16 * 8 + g8 * 4 + 0);
-              bits |= half2_pos_mask(o.y) & mask_pair_const(h16 * 8 + g8 * 4 + 1);
-              bits |= half2_pos_mask(o.z) & mask_pair_const(h16 * 8 + g8 * 4 + 2);
-              bits |= half2_pos_mask(o.w) & mask_pair_const(h16 * 8 + g8 * 4 + 3);
-            }
-            const int col = ch * 128 + cc * 32 + h16 * 16 + g8 * 8;
-            *reinterpret_cast<uint4*>(a_dst + (col >> 6) * kAChunk + swz[(col >> 3) & 7]) = o;
-          }
-          const int nxt = cc * 2 + h16 + 1;               // next 16-column block of this thread's 128 columns
-          if (nxt < 8) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              u[g] = __ldg(up + (size_t)(nxt * 4 + g) * p.n);
-              v[g] = __ldg(vp + nxt * 4 + g);
-            }
-          }
+          for (int g = 0; g < 4; ++g) u[(blk + 2) % 3][g] = __ldg(up + (size_t)((blk + 2) * 4 + g) * p.n);
         }
-        if (SAVE) mrow[cc] = bits;
-        tmem_st16(alo + cc * 16, lo);
+        float4 v[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) v[g] = __ldg(vp + blk * 4 + g);
+        const int h16 = blk & 1;
+#pragma unroll
+        for (int g8 = 0; g8 < 2; ++g8) {
+          const float4 u0 = u[blk % 3][2 * g8], u1 = u[blk % 3][2 * g8 + 1], v0 = v[2 * g8], v1 = v[2 * g8 + 1];
+          uint4 o;
+          uint32_t* l4 = lo + h16 * 8 + g8 * 4;
+          split_relu_half2(u0.x + v0.x, u0.y + v0.y, o.x, l4[0]);
+          split_relu_half2(u0.z + v0.z, u0.w + v0.w, o.y, l4[1]);
+          split_relu_half2(u1.x + v1.x, u1.y + v1.y, o.z, l4[2]);
+          split_relu_half2(u1.z + v1.z, u1.w + v1.w, o.w, l4[3]);
+          if (SAVE) {
+            bits |= half2_pos_mask(o.x) & mask_pair_const(h16 * 8 + g8 * 4 + 0);
+            bits |= half2_pos_mask(o.y) & mask_pair_const(h16 * 8 + g8 * 4 + 1);
+            bits |= half2_pos_mask(o.z) & mask_pair_const(h16 * 8 + g8 * 4 + 2);
+            bits |= half2_pos_mask(o.w) & mask_pair_const(h16 * 8 + g8 * 4 + 3);
+          }
+          const int col = ch * 128 + blk * 16 + g8 * 8;
+          *reinterpret_cast<uint4*>(a_dst + (col >> 6) * kAChunk + ((((col >> 3) & 7) ^ r7) << 4)) = o;
+        }
+        if (h16) {                                        // 32 columns = 16 tensor-memory columns per store
+          if (SAVE) mrow[blk >> 1] = bits;
+          bits = 0;
+          tmem_st16(alo + (blk >> 1) * 16, lo);
+        }
       }
       tmem_st_wait();
       fence_proxy_async_smem();
       if (SAVE && !p.skip_h1_image) {
         named_bar_sync(3, 256);
         if (gt == 0) {
-          bulk_s2g(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile, smem_u32(a_dst), kATile);
+          bulk_s2g(reinterpret_cast<char*>(p.saveH) + ((size_t)tile * 3 + 0) * kATile, smem_u32(smem + buf * kATile), kATile);
           bulk_commit();
           bulk_wait_read0();
         }
@@ -1144,7 +1146,7 @@ __global__ void __launch_bounds__(k3Threads, 1) rn_g_fwd3_kernel(const ChainPara
     if (SAVE && gt == 0) bulk_wait0();
   } else {
     // ================= epilogue warps =================
-    reg_inc<128>();
+    reg_inc<120>();
     const int q = warp & 3, ch = (warp - 4) >> 2, et = threadIdx.x - 128;
     const int row = q * 32 + lane;
     uint32_t swz[8];
