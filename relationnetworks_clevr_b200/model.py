@@ -230,8 +230,10 @@ class RN(nn.Module):
         if self.state_desc or os.environ.get("RN_B200_TEXT_STREAM", "1") == "0" or (self.text.use_kernel and self.text.hidden == 128):
             # (the question-encoder kernel is one short launch: nothing to gain from a side stream, and the step stays
             # a single-stream sequence that CUDA-graph capture takes as is)
+            ops.fork_point(img.device)             # the question encoder only needs the tokens: it may start now ...
+            qst = self.text(qst_idxs)              # ... on the auxiliary stream (ops.QuestionEncoderFunction)
             x = img if self.state_desc else self._objects(img)
-            qst = self.text(qst_idxs)
+            ops.join_aux(img.device)               # the relation op reads q
             return self.rl(x, qst)
         # The question encoder (PyTorch/cuDNN, a chain of small latency-bound kernels) runs on a side stream next to
         # the conv stack; autograd replays its backward on the same side stream, next to the conv backward.

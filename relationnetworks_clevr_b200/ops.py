@@ -40,6 +40,63 @@ def side_stream(device: torch.device) -> torch.cuda.Stream:
     return st
 
 
+# ---- auxiliary stream for the question encoder -----------------------------------------------------------------
+# The LSTM kernels are short, latency-bound launches that depend only on the tokens and their own parameters (forward)
+# or on dq (backward); the conv stack next to them is a chain of kernels that never fills the machine at small batches.
+# They run concurrently: the encoder's C-ABI calls are issued on an auxiliary stream that waits on a FORK POINT (an event
+# recorded on the main stream at the start of RN.forward / at the end of the relation backward, i.e. independent of the
+# order in which autograd happens to call the two backward nodes) and the main stream JOINS before the first consumer
+# (the relation forward; the optimiser).  No torch stream context is switched, so every tensor is allocated from -- and
+# returns to -- the main stream's pool, and under CUDA-graph capture the fork / join pair is captured as a parallel branch.
+_aux: Dict[int, dict] = {}
+
+
+def _aux_state(device: torch.device) -> dict:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _aux.get(idx)
+    if st is None:
+        st = {"stream": torch.cuda.Stream(device=idx), "fork": None, "join": None, "pending": False, "keep": []}
+        _aux[idx] = st
+    return st
+
+
+def fork_point(device: torch.device) -> None:
+    """Work issued on the auxiliary stream from now on may start once everything enqueued on the main stream so far is done."""
+    st = _aux_state(device)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    st["fork"] = ev
+
+
+def _aux_begin(device: torch.device) -> int:
+    st = _aux_state(device)
+    if st["fork"] is None:
+        fork_point(device)
+    st["stream"].wait_event(st["fork"])
+    return st["stream"].cuda_stream
+
+
+def _aux_end(device: torch.device, defer_join: bool, keep=()) -> None:
+    """`keep`: tensors the auxiliary-stream kernels touch.  They are held until the join, so the caching allocator (which
+    only knows the main stream) cannot hand their memory to main-stream work that would run concurrently."""
+    st = _aux_state(device)
+    ev = torch.cuda.Event()
+    ev.record(st["stream"])
+    st["join"], st["pending"], st["fork"] = ev, True, None
+    st["keep"].extend(keep)
+    if not defer_join:
+        join_aux(device)
+
+
+def join_aux(device: torch.device) -> None:
+    """The main stream waits for everything issued on the auxiliary stream (no-op when nothing is pending)."""
+    st = _aux.get(device.index if device.index is not None else torch.cuda.current_device())
+    if st is not None and st["pending"]:
+        torch.cuda.current_stream(device).wait_event(st["join"])
+        st["pending"] = False
+        st["keep"].clear()
+
+
 def _mark_for_side_consumers(t: torch.Tensor) -> None:
     """A gradient produced here may be consumed by a backward node running on the side stream: keep the caching
     allocator from recycling it before that stream is done with it."""
@@ -240,6 +297,7 @@ class RelationFunction(torch.autograd.Function):
                                         ctx.saved_buf.data_ptr(), dx.data_ptr(), dq.data_ptr(), ptr_array(dws),
                                         ptr_array(dbs), scratch.data_ptr(), _stream()), "rn_relation_bwd")
         _mark_for_side_consumers(dq)
+        fork_point(x_.device)          # dq and dx exist: the question-encoder backward may run next to the conv backward
         grads = []
         for dw, db in zip(_grad_returns(pw, dws), _grad_returns(pb, dbs)):
             grads += [dw, db]
@@ -337,6 +395,9 @@ class FHeadFunction(torch.autograd.Function):
         return (dxg, *_grad_returns(ctx.params, [dw1, db1, dw2, db2, dw3, db3]), None, None)
 
 
+use_aux_stream = os.environ.get("RN_B200_TEXT_STREAM", "1") != "0"
+
+
 def lstm_supported(B: int, T: int, V: int, E: int, H: int) -> bool:
     cfg = LstmCfg(B, T, V, E, H, 0)
     return bool(lib().rn_lstm_supported(C.byref(cfg)))
@@ -364,9 +425,12 @@ class QuestionEncoderFunction(torch.autograd.Function):
         check(lib().rn_lstm_workspace(C.byref(cfg), C.byref(sf), C.byref(cf)), "rn_lstm_workspace")
         saved = torch.empty(sf.value, dtype=torch.float32, device=tok.device)
         q = torch.empty(B, H, dtype=torch.float32, device=tok.device)
+        stream = _aux_begin(tok.device) if use_aux_stream else _stream()
         with _Timed("lstm_fwd"):
             check(lib().rn_lstm_fwd(C.byref(cfg), tok.data_ptr(), *[p.data_ptr() for p in ps], q.data_ptr(), saved.data_ptr(),
-                                    _stream()), "rn_lstm_fwd")
+                                    stream), "rn_lstm_fwd")
+        if use_aux_stream:
+            _aux_end(tok.device, defer_join=True, keep=(tok, saved, q, *ps))       # RN.forward joins before the relation op reads q
         if training:
             ctx.cfg = cfg
             ctx.scratch_floats = cf.value
@@ -381,10 +445,15 @@ class QuestionEncoderFunction(torch.autograd.Function):
         dq_ = _f32c(dq)
         grads = _grad_outputs(ctx.params, ps)
         scratch = _scratch_bytes(tok.device, "lstm", ctx.scratch_floats * 4)
+        stream = _aux_begin(tok.device) if use_aux_stream else _stream()
         with _Timed("lstm_bwd"):
             check(lib().rn_lstm_bwd(C.byref(ctx.cfg), tok.data_ptr(), ps[0].data_ptr(), ps[1].data_ptr(), ps[2].data_ptr(),
                                     dq_.data_ptr(), saved.data_ptr(), *[g.data_ptr() for g in grads], scratch.data_ptr(),
-                                    _stream()), "rn_lstm_bwd")
+                                    stream), "rn_lstm_bwd")
+        if use_aux_stream:
+            # with the optimiser's gradient sink active the join is deferred to FlatClipAdam.step(); otherwise (plain
+            # autograd users reading param.grad on the main stream) join right away
+            _aux_end(tok.device, defer_join=_sink is not None, keep=(tok, saved, dq_, scratch, *ps, *grads))
         return (None, *_grad_returns(ctx.params, grads))
 
 

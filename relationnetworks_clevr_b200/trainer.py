@@ -109,6 +109,7 @@ class FlatClipAdam:
                                    "flatten_parameters() called after the optimiser was built?)")
 
     def step(self) -> torch.Tensor:
+        ops.join_aux(self.flat.device)         # gradients written on the auxiliary stream (question encoder) are complete
         g = self.gather_grads()
         scale = allreduce_flat_(g)
         self.last_norm = ops.clip_adam_(self.flat, g, self.exp_avg, self.exp_avg_sq, 0, self.lr, self.clip_norm,
