@@ -231,7 +231,8 @@ class RN(nn.Module):
             # (the question-encoder kernel is one short launch: nothing to gain from a side stream, and the step stays
             # a single-stream sequence that CUDA-graph capture takes as is)
             ops.fork_point(img.device)             # the question encoder only needs the tokens: it may start now ...
-            qst = self.text(qst_idxs)              # ... on the auxiliary stream (ops.QuestionEncoderFunction)
+            with ops.defer_text_join():
+                qst = self.text(qst_idxs)          # ... on the auxiliary stream (ops.QuestionEncoderFunction), small batches
             x = img if self.state_desc else self._objects(img)
             ops.join_aux(img.device)               # the relation op reads q
             return self.rl(x, qst)

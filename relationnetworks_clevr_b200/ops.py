@@ -395,7 +395,25 @@ class FHeadFunction(torch.autograd.Function):
         return (dxg, *_grad_returns(ctx.params, [dw1, db1, dw2, db2, dw3, db3]), None, None)
 
 
+# The auxiliary stream pays when the batch is small (at 80 questions per GPU the conv kernels cover a fraction of the SMs:
+# measured 1.53 vs X ms per step); at 640 per GPU the encoder's 144 register-heavy CTAs take SMs away from the conv stack
+# and the step gets 2 % slower (8.11 vs 7.93 ms), so it is used below a batch threshold only.
 use_aux_stream = os.environ.get("RN_B200_TEXT_STREAM", "1") != "0"
+aux_stream_max_batch = int(os.environ.get("RN_B200_TEXT_STREAM_MAX_BATCH", "256"))
+_defer_forward_join = False      # set by RN.forward around its text call: it joins itself, before the relation op
+
+
+class defer_text_join:
+    """Context manager used by RN.forward: inside it the question encoder's forward leaves its join to the caller."""
+
+    def __enter__(self):
+        global _defer_forward_join
+        self.prev, _defer_forward_join = _defer_forward_join, True
+
+    def __exit__(self, *exc):
+        global _defer_forward_join
+        _defer_forward_join = self.prev
+        return False
 
 
 def lstm_supported(B: int, T: int, V: int, E: int, H: int) -> bool:
@@ -425,12 +443,14 @@ class QuestionEncoderFunction(torch.autograd.Function):
         check(lib().rn_lstm_workspace(C.byref(cfg), C.byref(sf), C.byref(cf)), "rn_lstm_workspace")
         saved = torch.empty(sf.value, dtype=torch.float32, device=tok.device)
         q = torch.empty(B, H, dtype=torch.float32, device=tok.device)
-        stream = _aux_begin(tok.device) if use_aux_stream else _stream()
+        aux = use_aux_stream and B <= aux_stream_max_batch
+        stream = _aux_begin(tok.device) if aux else _stream()
         with _Timed("lstm_fwd"):
             check(lib().rn_lstm_fwd(C.byref(cfg), tok.data_ptr(), *[p.data_ptr() for p in ps], q.data_ptr(), saved.data_ptr(),
                                     stream), "rn_lstm_fwd")
-        if use_aux_stream:
-            _aux_end(tok.device, defer_join=True, keep=(tok, saved, q, *ps))       # RN.forward joins before the relation op reads q
+        if aux:      # inside RN.forward the join is RN's (before the relation op reads q); standalone callers join here
+            _aux_end(tok.device, defer_join=_defer_forward_join, keep=(tok, saved, q, *ps))
+        ctx.aux = aux
         if training:
             ctx.cfg = cfg
             ctx.scratch_floats = cf.value
@@ -445,15 +465,18 @@ class QuestionEncoderFunction(torch.autograd.Function):
         dq_ = _f32c(dq)
         grads = _grad_outputs(ctx.params, ps)
         scratch = _scratch_bytes(tok.device, "lstm", ctx.scratch_floats * 4)
-        stream = _aux_begin(tok.device) if use_aux_stream else _stream()
+        # The auxiliary stream is only safe when this call allocates NOTHING: a block the caching allocator hands out here
+        # may have just been released by the conv backward, whose kernels are still running on the main stream (the fork
+        # point precedes them) -- measured: a fresh gradient tensor landed on the saved input image and corrupted
+        # dW(conv1).  With the optimiser's gradient sink every output is a slice of the flat gradient buffer.
+        aux = ctx.aux and _sink is not None and all(_sink_view(p) is not None for p in ctx.params) and dq_.data_ptr() == dq.data_ptr()
+        stream = _aux_begin(tok.device) if aux else _stream()
         with _Timed("lstm_bwd"):
             check(lib().rn_lstm_bwd(C.byref(ctx.cfg), tok.data_ptr(), ps[0].data_ptr(), ps[1].data_ptr(), ps[2].data_ptr(),
                                     dq_.data_ptr(), saved.data_ptr(), *[g.data_ptr() for g in grads], scratch.data_ptr(),
                                     stream), "rn_lstm_bwd")
-        if use_aux_stream:
-            # with the optimiser's gradient sink active the join is deferred to FlatClipAdam.step(); otherwise (plain
-            # autograd users reading param.grad on the main stream) join right away
-            _aux_end(tok.device, defer_join=_sink is not None, keep=(tok, saved, dq_, scratch, *ps, *grads))
+        if aux:      # the join is FlatClipAdam.step()'s
+            _aux_end(tok.device, defer_join=True, keep=(tok, saved, dq_, scratch, *ps, *grads))
         return (None, *_grad_returns(ctx.params, grads))
 
 
