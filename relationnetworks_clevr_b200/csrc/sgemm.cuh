@@ -210,7 +210,7 @@ inline int sgemm(bool at, bool bt, int M, int N, int K, const float* A, long lon
   dim3 grid(cdiv(M, bm), cdiv(N, bn), 1);
   int splits = 1;
   const long long tiles = (long long)grid.x * grid.y;
-  if (splitk_ws && K >= 2048 && tiles < 2LL * sm_count()) {
+  if (splitk_ws && K >= 1024 && tiles < 2LL * sm_count()) {
     splits = (int)min((long long)cdiv(K, 256), max(1LL, (2LL * sm_count()) / tiles));
     while (splits > 1 && (size_t)splits * M * N > splitk_ws_floats) --splits;
   }
