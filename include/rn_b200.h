@@ -150,7 +150,12 @@ typedef struct rn_conv_cfg {
   float momentum;    /* BatchNorm momentum (0.1) */
   int32_t img_u8;    /* 1: `img` is uint8 [B,3,S,S] (raw pixels); the first layer computes x = u / 255 (torchvision ToTensor,
                       * train.py:182-188) while staging -- a quarter of the host-to-device bytes.  0: fp32 in [0,1] */
+  int32_t flags;     /* RN_CONV_FLAG_*; 0 = default kernels */
 } rn_conv_cfg;
+
+/* The convolutions run on the tensor cores (mma.sync, TF32 operands, error-compensated 3-pass split: fp32-level accuracy)
+ * when side % 64 == 0; this flag forces the fp32 SIMT kernels that serve every other shape (A/B comparisons, tests). */
+#define RN_CONV_FLAG_SIMT 1
 
 /* Per-layer parameter block, host array of RN_CONV_LAYERS entries (device pointers inside). */
 typedef struct rn_conv_layer {

@@ -135,12 +135,18 @@ BN_MOMENTUM = 0.1   # nn.BatchNorm2d default
 
 
 def conv_features(p: Params, img: torch.Tensor, training: bool,
-                  running_out: Optional[Params] = None) -> torch.Tensor:
+                  running_out: Optional[Params] = None, pre_out: Optional[list] = None,
+                  flip: Optional[dict] = None) -> torch.Tensor:
     """4 x [conv3x3 stride 2 pad 1 -> BatchNorm(24) -> ReLU]  (model.py:22-36).
 
     training=True normalises with biased batch statistics and, if ``running_out`` is given,
     stores the updated running stats there (momentum 0.1, unbiased variance) as
-    nn.BatchNorm2d does.  [B,3,S,S] -> [B,24,S/16,S/16]."""
+    nn.BatchNorm2d does.  [B,3,S,S] -> [B,24,S/16,S/16].
+
+    Conditioning diagnostics for the parity tests (not part of the reference's arithmetic): ``pre_out`` collects
+    the four ReLU pre-activations; ``flip`` = {layer (1-based): bool mask} evaluates the listed elements with the
+    OTHER branch of the ReLU (value min(x, 0) ~ 0, derivative 1 - 1[x > 0]) -- what any evaluation whose round-off
+    moves a pre-activation across zero computes."""
     x = img
     for i in range(1, 5):
         x = F.conv2d(x, p[f"conv.conv{i}.weight"], p[f"conv.conv{i}.bias"], stride=2, padding=1)
@@ -159,7 +165,12 @@ def conv_features(p: Params, img: torch.Tensor, training: bool,
             var = p[f"conv.batchNorm{i}.running_var"]
         x = (x - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + BN_EPS)
         x = x * gamma[None, :, None, None] + beta[None, :, None, None]
-        x = torch.relu(x)
+        if pre_out is not None:
+            pre_out.append(x.detach())
+        if flip is not None and i in flip:
+            x = torch.where(flip[i], x - torch.relu(x), torch.relu(x))
+        else:
+            x = torch.relu(x)
     return x
 
 

@@ -31,7 +31,7 @@ class FCfg(C.Structure):
 
 class ConvCfg(C.Structure):
     _fields_ = [("B", C.c_int32), ("side", C.c_int32), ("training", C.c_int32), ("eps", C.c_float),
-                ("momentum", C.c_float), ("img_u8", C.c_int32)]
+                ("momentum", C.c_float), ("img_u8", C.c_int32), ("flags", C.c_int32)]
 
 
 class ConvLayer(C.Structure):

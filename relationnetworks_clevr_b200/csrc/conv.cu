@@ -680,6 +680,48 @@ conv_dgrad_kernel(const float* __restrict__ yout, const float* __restrict__ dAou
   }
 }
 
+}  // namespace rn
+
+#include "conv_tc.cuh"
+
+namespace rn {
+
+// ---- tensor-core path (conv_tc.cuh): side % 64 == 0 keeps every layer's rows float4-aligned -------------------------
+static bool conv_tc_ok(const rn_conv_cfg& c) { return c.side % 64 == 0 && !(c.flags & RN_CONV_FLAG_SIMT); }
+
+struct TcGrid {
+  int tw, tiles_x, tiles, units, grid;
+};
+// fwd / dgrad: unit = TW x TW outputs (quads); wgrad: 8 x 16 outputs (TW = 16) or two 8x8 images
+static TcGrid tc_grid(int B, int hout, int unit_rows16, int nimg8) {
+  TcGrid g;
+  g.tw = hout <= 8 ? 8 : 16;
+  if (g.tw == 16) {
+    g.tiles_x = cdiv(hout, 16);
+    g.tiles = g.tiles_x * cdiv(hout, unit_rows16);
+    g.units = B * g.tiles;
+  } else {
+    g.tiles_x = 1;
+    g.tiles = 1;
+    g.units = cdiv(B, nimg8);
+  }
+  const int slots = 2 * sm_count();
+  const int per = cdiv(g.units, slots);
+  g.grid = cdiv(g.units, per);
+  return g;
+}
+
+template <int CIN, int TW, bool U8>
+static int launch_fwd_tc(const TcGrid& g, const void* in, const float* in_aff, const rn_conv_layer& L, float* y, float* part,
+                         int B, int hin, int hout, cudaStream_t st) {
+  const size_t smem = ctc::FwdCfg<CIN, TW>::SMEM;
+  RN_CUDA(cudaFuncSetAttribute(ctc::conv_fwd_tc_kernel<CIN, TW, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctc::conv_fwd_tc_kernel<CIN, TW, U8><<<g.grid, 256, smem, st>>>(in, in_aff, L.w, L.bias, y, part, B, hin, hout, g.tiles_x,
+                                                                 g.tiles, g.units);
+  RN_LAUNCH_CHECK("conv_fwd_tc_kernel");
+  return RN_OK;
+}
+
 constexpr int kRedChunks = 64;      // row chunks of the two-stage fixed-order reduction of the wgrad partials
 
 struct ConvPlan {
@@ -757,14 +799,22 @@ extern "C" int rn_conv_fwd(const rn_conv_cfg* cfg, const void* img_any, const rn
     const int hin = p.h[l], hout = p.h[l + 1], tx = cdiv(hout, kTile);
     dim3 grid(p.tiles[l], cfg->B);
     float* part = cfg->training ? scratch : nullptr;
-    if (l == 0 && cfg->img_u8)
+    int nblk = p.tiles[l] * cfg->B;
+    if (conv_tc_ok(*cfg)) {
+      const TcGrid g = tc_grid(cfg->B, hout, 16, 4);
+      nblk = g.grid;
+      if (l == 0 && cfg->img_u8) RN_TRY((launch_fwd_tc<3, 16, true>(g, in, in_aff, L[l], y, part, cfg->B, hin, hout, st)));
+      else if (l == 0) RN_TRY((launch_fwd_tc<3, 16, false>(g, in, in_aff, L[l], y, part, cfg->B, hin, hout, st)));
+      else if (g.tw == 16) RN_TRY((launch_fwd_tc<kC, 16, false>(g, in, in_aff, L[l], y, part, cfg->B, hin, hout, st)));
+      else RN_TRY((launch_fwd_tc<kC, 8, false>(g, in, in_aff, L[l], y, part, cfg->B, hin, hout, st)));
+    } else if (l == 0 && cfg->img_u8)
       conv_fwd_kernel<3, true><<<grid, 256, 0, st>>>(in, in_aff, L[l].w, L[l].bias, y, part, hin, hout, tx);
     else if (l == 0)
       conv_fwd_kernel<3><<<grid, 256, 0, st>>>(in, in_aff, L[l].w, L[l].bias, y, part, hin, hout, tx);
     else
       conv_fwd_kernel<kC><<<grid, 256, 0, st>>>(in, in_aff, L[l].w, L[l].bias, y, part, hin, hout, tx);
     RN_LAUNCH_CHECK("conv_fwd_kernel");
-    bn_finalize_kernel<<<kC, 256, 0, st>>>(scratch, p.tiles[l] * cfg->B, (double)cfg->B * hout * hout, L[l].gamma,
+    bn_finalize_kernel<<<kC, 256, 0, st>>>(scratch, nblk, (double)cfg->B * hout * hout, L[l].gamma,
                                              L[l].beta, L[l].running_mean, L[l].running_var, aff, cfg->eps,
                                              cfg->momentum, cfg->training);
     RN_LAUNCH_CHECK("bn_finalize_kernel");
@@ -818,7 +868,29 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
     const float* in_aff = l == 0 ? nullptr : saved + p.aff_off[l - 1];
     dim3 grid(p.tiles[l], cfg->B);
     const int cin = l == 0 ? 3 : kC;
-    if (l == 0 && cfg->img_u8) {
+    const bool tc = conv_tc_ok(*cfg);
+    int nblk = p.tiles[l] * cfg->B;
+    if (tc && l == 0) {
+      const TcGrid g = tc_grid(cfg->B, hout, 16, 1);
+      nblk = g.grid;
+      const size_t smem = ctc::Wg3Cfg::SMEM;
+      if (cfg->img_u8)
+        ctc::conv_wgrad3_tc_kernel<true><<<g.grid, 256, smem, st>>>(in, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+      else
+        ctc::conv_wgrad3_tc_kernel<false><<<g.grid, 256, smem, st>>>(in, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+    } else if (tc) {
+      const TcGrid g = tc_grid(cfg->B, hout, 8, 2);
+      nblk = g.grid;
+      if (g.tw == 16) {
+        const size_t smem = ctc::WgCfg<16>::SMEM;
+        RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctc::conv_wgrad_tc_kernel<16><<<g.grid, 224, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+      } else {
+        const size_t smem = ctc::WgCfg<8>::SMEM;
+        RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctc::conv_wgrad_tc_kernel<8><<<g.grid, 224, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+      }
+    } else if (l == 0 && cfg->img_u8) {
       const size_t smem = wgrad_smem_bytes<3>();
       RN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       conv_wgrad_kernel<3, true><<<grid, 256, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, hin, hout, tx);
@@ -835,7 +907,7 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
     {
       // dW = sum over blocks of the partials, two stages so the reduction itself fills the machine:
       // [nblk][N] -> [64][N] -> [N]  (both fixed order: deterministic)
-      const int N = kC * cin * 9, nblk = p.tiles[l] * cfg->B;
+      const int N = kC * cin * 9;
       float* red_tmp = wpart + round_up((size_t)wpart_floats, 64);
       if (nblk >= 4 * kRedChunks) {
         const int per = cdiv(nblk, kRedChunks);
@@ -853,7 +925,20 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
       // data gradient into dA (now sized for layer l-1's output == this layer's input)
       const int qt = cdiv(hout, kTile);
       // reads (y_l, dA_l), writes dA_{l-1} into the other buffer
-      conv_dgrad_kernel<<<dim3(qt * qt, cfg->B), 256, 0, st>>>(y, dA, aff, coef, L[l].w, dA_next, hin, hout, qt);
+      if (tc) {
+        const TcGrid g = tc_grid(cfg->B, hout, 16, 4);
+        if (g.tw == 16) {
+          const size_t smem = ctc::DgCfg<16>::SMEM;
+          RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          ctc::conv_dgrad_tc_kernel<16><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+        } else {
+          const size_t smem = ctc::DgCfg<8>::SMEM;
+          RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          ctc::conv_dgrad_tc_kernel<8><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+        }
+      } else {
+        conv_dgrad_kernel<<<dim3(qt * qt, cfg->B), 256, 0, st>>>(y, dA, aff, coef, L[l].w, dA_next, hin, hout, qt);
+      }
       RN_LAUNCH_CHECK("conv_dgrad_kernel");
       float* t = dA; dA = dA_next; dA_next = t;
     }

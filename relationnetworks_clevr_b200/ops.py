@@ -227,6 +227,8 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 REL_FLAG_FWD_2PASS = 1
 REL_FLAG_DGRAD_2PASS = 2
 relation_flags = int(os.environ.get("RN_B200_REL_FLAGS", "0"))
+# rn_conv_cfg.flags (RN_CONV_FLAG_*): 1 = fp32 SIMT convolutions instead of the tensor-core ones (tests, A/B timing)
+conv_flags = int(os.environ.get("RN_B200_CONV_FLAGS", "0"))
 
 
 def relation_cfg(B, n, k, Q, G, L, qinj, precision: str, training: bool, flags=None) -> RelationCfg:
@@ -509,7 +511,7 @@ class ConvObjectsFunction(torch.autograd.Function):
         B, cin, side, side2 = img_.shape
         if cin != 3 or side != side2:
             raise RuntimeError(f"expected [B,3,S,S] images, got {tuple(img_.shape)}")
-        cfg = ConvCfg(B, side, int(training), float(eps), float(momentum), int(img_u8))
+        cfg = ConvCfg(B, side, int(training), float(eps), float(momentum), int(img_u8), conv_flags)
         sf, cf = C.c_size_t(), C.c_size_t()
         check(lib().rn_conv_workspace(C.byref(cfg), C.byref(sf), C.byref(cf)), "rn_conv_workspace")
         saved = torch.empty(sf.value, dtype=torch.float32, device=img.device)

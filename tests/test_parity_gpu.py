@@ -291,7 +291,9 @@ def _conv_params(seed):
     return {k_: v for k_, v in p.items() if k_.startswith("conv.")}
 
 
-@pytest.mark.parametrize("B,side", [(3, 32), (2, 64), (2, 128), (1, 192)])
+# side % 64 == 0 runs the tensor-core convolutions (TF32 x3 split), other sides the fp32 SIMT kernels; batches that are
+# not multiples of the images-per-block of the 8x8 / 4x4 layers (4 forward, 2 weight gradient) exercise the image masks
+@pytest.mark.parametrize("B,side", [(3, 32), (2, 64), (5, 64), (2, 128), (5, 128), (1, 192), (1, 256)])
 @pytest.mark.parametrize("training", [True, False])
 def test_conv_objects_match_oracle(B, side, training):
     p = _conv_params(side + B)
@@ -299,10 +301,26 @@ def test_conv_objects_match_oracle(B, side, training):
     d = side // 16
     dobj = torch.randn(B, d * d, 26, generator=torch.Generator().manual_seed(1))
     p64 = {k_: (v.double().requires_grad_("running" not in k_)) for k_, v in p.items()}
-    running = {}
-    feat = O.conv_features(p64, img.double(), training, running)
+    running, pre = {}, []
+    feat = O.conv_features(p64, img.double(), training, running, pre_out=pre)
     obj_ref = O.objects_from_features(feat)
     obj_ref.backward(dobj.double())
+    # Conditioning: a ReLU pre-activation within fp32 round-off of zero (|pre| < 1e-7 max|pre|, i.e. ~2 ulp) takes either
+    # branch depending on the fp32 evaluation order, and with these tiny batches ONE flipped mask moves the conv1 / conv2
+    # weight gradients by 3e-3 .. 3e-2 of their max-norm (sums over few, nearly cancelling terms).  Each such element's
+    # effect, measured by re-running the fp64 oracle with that element on the other branch, is added to the tolerance.
+    floor = {}
+    fragile = [(i + 1, idx) for i, x in enumerate(pre)
+               for idx in (x.abs() < 1e-7 * x.abs().max()).nonzero().tolist()]
+    assert len(fragile) <= 8, "test inputs are degenerate"
+    for layer, idx in fragile:
+        mask = torch.zeros_like(pre[layer - 1], dtype=torch.bool)
+        mask[tuple(idx)] = True
+        q64 = {k_: (v.detach().clone().requires_grad_("running" not in k_)) for k_, v in p64.items()}
+        O.objects_from_features(O.conv_features(q64, img.double(), training, flip={layer: mask})).backward(dobj.double())
+        for k_, v in q64.items():
+            if v.grad is not None and float(p64[k_].grad.abs().max()) > 0:
+                floor[k_] = floor.get(k_, 0.0) + float(O.rel_err(v.grad, p64[k_].grad))
     m = R.ConvInputModel()
     m.load_state_dict({k_[len("conv."):]: v for k_, v in p.items()}, strict=False)
     m.to(DEV).train(training)
@@ -314,7 +332,7 @@ def test_conv_objects_match_oracle(B, side, training):
         if name.startswith("conv") and name.endswith("bias") and training:
             assert float(prm.grad.abs().max()) == 0.0      # exactly zero by construction (BN removes it)
             continue
-        assert O.rel_err(prm.grad.cpu(), ref) < 5e-4, name
+        assert O.rel_err(prm.grad.cpu(), ref) < 5e-4 + 1.5 * floor.get("conv." + name, 0.0), name
     if training:
         for i in range(1, 5):
             for s in ("running_mean", "running_var"):
@@ -325,6 +343,37 @@ def test_conv_objects_match_oracle(B, side, training):
         m.eval()
         f2 = m(img.to(DEV))
         assert f2.shape == (B, 24, d, d)
+
+
+@pytest.mark.parametrize("B,side", [(13, 128), (3, 192)])
+def test_conv_tensor_core_matches_simt(B, side):
+    """The tensor-core convolutions (mma.sync TF32 with the 3-pass hi/lo split) against this library's fp32 SIMT kernels on
+    the same inputs: both are fp32-level evaluations of the same sums (1e-5 forward, 1e-4 gradients), over enough blocks
+    that the persistent kernels loop over several units."""
+    p = _conv_params(side + B)
+    img = O.uniform_images(B, side, seed=side + 1).to(DEV)
+    d = side // 16
+    dobj = torch.randn(B, d * d, 26, generator=torch.Generator().manual_seed(3)).to(DEV)
+    res = []
+    saved_flags = ops.conv_flags
+    try:
+        for flags in (0, 1):
+            ops.conv_flags = flags
+            m = R.ConvInputModel()
+            m.load_state_dict({k_[len("conv."):]: v for k_, v in p.items()}, strict=False)
+            m.to(DEV).train()
+            obj = m.objects(img)
+            obj.backward(dobj)
+            res.append({"obj": obj.detach(), **{n: prm.grad for n, prm in m.named_parameters()},
+                        **{n: b_.clone() for n, b_ in m.named_buffers() if "running" in n}})
+    finally:
+        ops.conv_flags = saved_flags
+    for name in res[0]:
+        a, b_ = res[0][name], res[1][name]
+        if float(b_.abs().max()) == 0.0:
+            assert float(a.abs().max()) == 0.0, name
+            continue
+        assert O.rel_err(a.cpu(), b_.cpu()) < (1e-5 if name == "obj" or "running" in name else 1e-4), name
 
 
 @pytest.mark.parametrize("side", [64, 128])
