@@ -21,9 +21,13 @@
 namespace rn {
 namespace ctc {
 
+// x = hi + lo, hi = x rounded to TF32 (10 explicit mantissa bits).  cvt.rna.tf32.f32 has no SASS instruction on sm_100a: it
+// expands to add / inf-test / select / mask (measured 12.0 vs 10.1 cycles per MMA in the 3-pass loop,
+// tests/micro/mma_sync_rate2.cu), so the rounding is done by hand -- round half away from zero on the magnitude, two
+// integer operations; activations and weights are finite and far from FLT_MAX, so no overflow case exists.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  lo = __float_as_uint(x - __uint_as_float(hi));      // the MMA ignores the low 13 bits of lo
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));      // exact; the MMA ignores the low 13 bits of lo (2^-21 relative)
 }
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
@@ -39,6 +43,18 @@ __device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], con
   mma_tf32(c, al[0], al[1], al[2], al[3], bh0, bh1);
   mma_tf32(c, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
   mma_tf32(c, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+}
+
+// the same for the three n-tiles of one A fragment, PASS-major: consecutive MMAs are independent (a dependent
+// back-to-back chain on one accumulator leaves the tensor pipe idle for the MMA latency)
+__device__ __forceinline__ void mma3x3(float (&c)[3][4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                       const uint32_t (&bh)[3][2], const uint32_t (&bl)[3][2]) {
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt) mma_tf32(c[nt], al[0], al[1], al[2], al[3], bh[nt][0], bh[nt][1]);
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt) mma_tf32(c[nt], ah[0], ah[1], ah[2], ah[3], bl[nt][0], bl[nt][1]);
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt) mma_tf32(c[nt], ah[0], ah[1], ah[2], ah[3], bh[nt][0], bh[nt][1]);
 }
 
 constexpr int pad32(int x, int r) { return x + ((r - x % 32) + 32) % 32; }   // smallest y >= x with y % 32 == r
@@ -217,16 +233,33 @@ struct FwdCfg {
 struct UnitPos {
   int b0, r0, c0;        // first image, first output row / column (quad row / column for the data gradient)
 };
+// Walk over the block's units u = blockIdx.x + k * gridDim.x, u = image group * tiles + tile, without divisions in the
+// loop: (group, tile) advance by the precomputed (gridDim.x / tiles, gridDim.x % tiles); tile -> (row, column) through a
+// 16-bit reciprocal (exact: tile * tiles_x < 2^16).
 template <int NIMG, int TH, int TWID>
-__device__ __forceinline__ UnitPos unit_pos(int u, int tiles, int tiles_x) {
-  UnitPos p;
-  const int bg = u / tiles, tile = u - bg * tiles;
-  const int ty = tile / tiles_x;
-  p.b0 = bg * NIMG;
-  p.r0 = ty * TH;
-  p.c0 = (tile - ty * tiles_x) * TWID;
-  return p;
-}
+struct UnitWalk {
+  int bg, tile, dbg, dtile, tiles, tiles_x, inv;
+  __device__ __forceinline__ UnitWalk(int tiles_, int tiles_x_) : tiles(tiles_), tiles_x(tiles_x_) {
+    bg = blockIdx.x / tiles;
+    tile = blockIdx.x - bg * tiles;
+    dbg = gridDim.x / tiles;
+    dtile = gridDim.x - dbg * tiles;
+    inv = (65536 + tiles_x - 1) / tiles_x;
+  }
+  __device__ __forceinline__ UnitPos pos() const {
+    UnitPos p;
+    const int ty = (tile * inv) >> 16;
+    p.b0 = bg * NIMG;
+    p.r0 = ty * TH;
+    p.c0 = (tile - ty * tiles_x) * TWID;
+    return p;
+  }
+  __device__ __forceinline__ void next() {
+    bg += dbg;
+    tile += dtile;
+    if (tile >= tiles) { tile -= tiles; ++bg; }
+  }
+};
 
 template <int CIN, int TW, bool U8>
 __global__ void __launch_bounds__(256, 2)
@@ -303,7 +336,8 @@ conv_fwd_tc_kernel(const void* __restrict__ in, const float* __restrict__ in_aff
 
   __syncthreads();                       // affs (and the weight fragments) are visible
   int u = blockIdx.x, ch = 0, buf = 0;
-  UnitPos cur = unit_pos<F::NIMG, TW, TW>(u < units ? u : 0, tiles, tiles_x);
+  UnitWalk<F::NIMG, TW, TW> walk(tiles, tiles_x);
+  UnitPos cur = walk.pos();
   if (u < units) {
     issue(cur, 0);
     stg.commit(patch, aff_s, tid);
@@ -318,7 +352,8 @@ conv_fwd_tc_kernel(const void* __restrict__ in, const float* __restrict__ in_aff
     if (nch == NCHUNK) {
       nch = 0;
       nu = u + gridDim.x;
-      if (nu < units) nxt = unit_pos<F::NIMG, TW, TW>(nu, tiles, tiles_x);
+      walk.next();
+      nxt = walk.pos();
     }
     const bool has_next = nu < units;
     if (has_next) issue(nxt, nch);
@@ -342,8 +377,7 @@ conv_fwd_tc_kernel(const void* __restrict__ in, const float* __restrict__ in_aff
           split_tf32(pa[so[j][1] + toff], ah[1], al[1]);
           split_tf32(pa[so[j][0] + toff + 4 * PS], ah[2], al[2]);
           split_tf32(pa[so[j][1] + toff + 4 * PS], ah[3], al[3]);
-#pragma unroll
-          for (int nt = 0; nt < 3; ++nt) mma3(acc[j][nt], ah, al, bh[nt][0], bh[nt][1], bl[nt][0], bl[nt][1]);
+          mma3x3(acc[j], ah, al, bh, bl);
         }
       }
     } else {
@@ -356,8 +390,7 @@ conv_fwd_tc_kernel(const void* __restrict__ in, const float* __restrict__ in_aff
           split_tf32(pb[koff[s][0] + so[j][1]], ah[1], al[1]);
           split_tf32(pb[koff[s][1] + so[j][0]], ah[2], al[2]);
           split_tf32(pb[koff[s][1] + so[j][1]], ah[3], al[3]);
-#pragma unroll
-          for (int nt = 0; nt < 3; ++nt) mma3(acc[j][nt], ah, al, wr_h[s][nt][0], wr_h[s][nt][1], wr_l[s][nt][0], wr_l[s][nt][1]);
+          mma3x3(acc[j], ah, al, wr_h[s], wr_l[s]);
         }
     }
 
@@ -504,8 +537,9 @@ conv_wgrad_tc_kernel(const float* __restrict__ in, const float* __restrict__ in_
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
 
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const UnitPos up = unit_pos<W::NIMG, 8, 16>(u, tiles, tiles_x);
+  UnitWalk<W::NIMG, 8, 16> walk(tiles, tiles_x);
+  for (int u = blockIdx.x; u < units; u += gridDim.x, walk.next()) {
+    const UnitPos up = walk.pos();
     __syncthreads();                         // the previous unit's fragments have been read (and affs / bnc are visible)
     // input patch in two passes (bounds the registers of the staging): TW = 16: rows 0..8 / 9..16 of all 24 channels
     // (thread -> one channel plane and vector column, walking down the rows), TW = 8: channels 0..11 / 12..23
@@ -569,8 +603,7 @@ conv_wgrad_tc_kernel(const float* __restrict__ in, const float* __restrict__ in_
         split_tf32(patch[arow[mt][1] + poff], ah[1], al[1]);
         split_tf32(patch[arow[mt][0] + poff + 4], ah[2], al[2]);
         split_tf32(patch[arow[mt][1] + poff + 4], ah[3], al[3]);
-#pragma unroll
-        for (int nt = 0; nt < 3; ++nt) mma3(acc[mt][nt], ah, al, bh[nt][0], bh[nt][1], bl[nt][0], bl[nt][1]);
+        mma3x3(acc[mt], ah, al, bh, bl);
       }
     }
   }
@@ -637,8 +670,9 @@ conv_wgrad3_tc_kernel(const void* __restrict__ in, const float* __restrict__ you
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
 
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const UnitPos up = unit_pos<1, 16, 16>(u, tiles, tiles_x);
+  UnitWalk<1, 16, 16> walk(tiles, tiles_x);
+  for (int u = blockIdx.x; u < units; u += gridDim.x, walk.next()) {
+    const UnitPos up = walk.pos();
     __syncthreads();
     {
       PatchStager<16, 1, 3, Wg3Cfg::NR, PS, 0, 256, U8> stg;
@@ -678,14 +712,22 @@ conv_wgrad3_tc_kernel(const void* __restrict__ in, const float* __restrict__ you
       split_tf32(dys[(g + 16) * LD + px], ah[1][0], al[1][0]);
       split_tf32(dys[(g + 16) * LD + px + 4], ah[1][2], al[1][2]);
       ah[1][1] = al[1][1] = ah[1][3] = al[1][3] = 0u;
+      uint32_t bh[4][2], bl[4][2];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(patch[noff[nt] + poff], bh0, bl0);
-        split_tf32(patch[noff[nt] + poff + 4], bh1, bl1);
-        mma3(acc[0][nt], ah[0], al[0], bh0, bh1, bl0, bl1);
-        mma3(acc[1][nt], ah[1], al[1], bh0, bh1, bl0, bl1);
+        split_tf32(patch[noff[nt] + poff], bh[nt][0], bl[nt][0]);
+        split_tf32(patch[noff[nt] + poff + 4], bh[nt][1], bl[nt][1]);
       }
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const uint32_t (&a)[4] = pass == 0 ? al[mt] : ah[mt];
+            const uint32_t (&b)[2] = pass == 1 ? bl[nt] : bh[nt];
+            mma_tf32(acc[mt][nt], a[0], a[1], a[2], a[3], b[0], b[1]);
+          }
     }
   }
 
@@ -773,8 +815,9 @@ conv_dgrad_tc_kernel(const float* __restrict__ yout, const float* __restrict__ d
   const int s_lane = tid / POS, s_pos = tid - s_lane * POS;
   const int s_r = s_pos / PERROW, s_v = s_pos - s_r * PERROW;
 
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const UnitPos up = unit_pos<D::NIMG, TW, TW>(u, tiles, tiles_x);
+  UnitWalk<D::NIMG, TW, TW> walk(tiles, tiles_x);
+  for (int u = blockIdx.x; u < units; u += gridDim.x, walk.next()) {
+    const UnitPos up = walk.pos();
     __syncthreads();                       // previous unit consumed (first pass: wsm / bnc visible after the next barrier)
     if (s_lane < LANES) {
       const int oh = up.r0 + s_r, ow = up.c0 + (s_v < TW / 4 ? 4 * s_v : TW);
@@ -831,12 +874,14 @@ conv_dgrad_tc_kernel(const float* __restrict__ yout, const float* __restrict__ d
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             if (p < NP[sh]) {
+              uint32_t bh[3][2], bl[3][2];
 #pragma unroll
               for (int nt = 0; nt < 3; ++nt) {
                 const float4 wv = wq[((TAPS[sh][p] * 3 + ks) * 3 + nt) * 32 + lane];
-                mma3(acc[CLS[sh][p]][nt], ah, al, __float_as_uint(wv.x), __float_as_uint(wv.y), __float_as_uint(wv.z),
-                     __float_as_uint(wv.w));
+                bh[nt][0] = __float_as_uint(wv.x); bh[nt][1] = __float_as_uint(wv.y);
+                bl[nt][0] = __float_as_uint(wv.z); bl[nt][1] = __float_as_uint(wv.w);
               }
+              mma3x3(acc[CLS[sh][p]], ah, al, bh, bl);
             }
           }
         }
