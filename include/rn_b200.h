@@ -153,9 +153,14 @@ typedef struct rn_conv_cfg {
   int32_t flags;     /* RN_CONV_FLAG_*; 0 = default kernels */
 } rn_conv_cfg;
 
-/* The convolutions run on the tensor cores (mma.sync, TF32 operands, error-compensated 3-pass split: fp32-level accuracy)
- * when side % 64 == 0; this flag forces the fp32 SIMT kernels that serve every other shape (A/B comparisons, tests). */
+/* side % 64 == 0: the BACKWARD convolutions (weight and data gradients) run on the tensor cores (mma.sync, TF32 operands,
+ * error-compensated 3-pass split: 2^-21 relative per product).  The FORWARD convolutions stay on the fp32 SIMT kernels by
+ * default: their rounding decides the ReLU masks of the whole stack, and a 2^-21 evaluation flips ~10x more near-zero
+ * pre-activations than a 2^-24 one (measured on the trained checkpoint: conv2.weight gradient 6e-3 instead of < 1e-3).
+ * RN_CONV_FLAG_SIMT forces the SIMT kernels everywhere (they also serve every other side); RN_CONV_FLAG_TC_FWD opts the
+ * forward into the tensor-core kernels (20 % faster forward, reduced mask fidelity). */
 #define RN_CONV_FLAG_SIMT 1
+#define RN_CONV_FLAG_TC_FWD 2
 
 /* Per-layer parameter block, host array of RN_CONV_LAYERS entries (device pointers inside). */
 typedef struct rn_conv_layer {

@@ -731,6 +731,7 @@ struct ConvPlan {
   size_t saved_floats;
   int tiles[RN_CONV_LAYERS];        // 16x16 output tiles per image
   size_t scratch_floats;
+  size_t spart_floats, wpart_floats;   // BatchNorm / weight-gradient partial regions of `scratch`
 };
 
 static ConvPlan make_plan(const rn_conv_cfg& c) {
@@ -754,11 +755,16 @@ static ConvPlan make_plan(const rn_conv_cfg& c) {
   size_t wpart = 0, spart = 0;
   for (int l = 0; l < RN_CONV_LAYERS; ++l) {
     const size_t cin = l == 0 ? 3 : kC;
-    wpart = std::max(wpart, (size_t)c.B * p.tiles[l] * kC * cin * 9);
-    spart = std::max(spart, (size_t)c.B * p.tiles[l] * 2 * kC);
+    // per-block weight-gradient / BatchNorm partials: one per 16x16 tile (SIMT kernels) or one per persistent block of the
+    // tensor-core kernels (at most two blocks per SM, never more than their 8-row units)
+    const size_t tc_blocks = std::min<size_t>((size_t)c.B * cdiv(p.h[l + 1], 16) * cdiv(p.h[l + 1], 8), (size_t)2 * sm_count());
+    const size_t blocks = std::max<size_t>((size_t)c.B * p.tiles[l], tc_blocks);
+    wpart = std::max(wpart, blocks * kC * cin * 9);
+    spart = std::max(spart, blocks * 2 * kC);
   }
-  p.scratch_floats = 2 * big + round_up(std::max(spart, (size_t)c.B * kC * 2), 64) + 64 * 4 + round_up(wpart, 64) +
-                     (size_t)kRedChunks * kC * kC * 9;
+  p.spart_floats = round_up(std::max(spart, (size_t)c.B * kC * 2), 64);
+  p.wpart_floats = round_up(wpart, 64);
+  p.scratch_floats = 2 * big + p.spart_floats + 64 * 4 + p.wpart_floats + (size_t)kRedChunks * kC * kC * 9;
   return p;
 }
 
@@ -800,7 +806,7 @@ extern "C" int rn_conv_fwd(const rn_conv_cfg* cfg, const void* img_any, const rn
     dim3 grid(p.tiles[l], cfg->B);
     float* part = cfg->training ? scratch : nullptr;
     int nblk = p.tiles[l] * cfg->B;
-    if (conv_tc_ok(*cfg)) {
+    if (conv_tc_ok(*cfg) && (cfg->flags & RN_CONV_FLAG_TC_FWD)) {
       const TcGrid g = tc_grid(cfg->B, hout, 16, 4);
       nblk = g.grid;
       if (l == 0 && cfg->img_u8) RN_TRY((launch_fwd_tc<3, 16, true>(g, in, in_aff, L[l], y, part, cfg->B, hin, hout, st)));
@@ -839,13 +845,9 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
   float* dA = scratch;
   float* dA_next = scratch + big;      // BatchNorm backward is applied on the fly by the consumers: no dy buffer
   float* bnpart = dA_next + big;
-  size_t spart = 0;
-  for (int l = 0; l < RN_CONV_LAYERS; ++l) spart = std::max(spart, (size_t)cfg->B * p.tiles[l] * 2 * kC);
-  float* coef = bnpart + round_up(std::max(spart, (size_t)cfg->B * kC * 2), 64);
+  float* coef = bnpart + p.spart_floats;
   float* wpart = coef + 64 * 4;
-  size_t wpart_floats = 0;
-  for (int l = 0; l < RN_CONV_LAYERS; ++l)
-    wpart_floats = std::max(wpart_floats, (size_t)cfg->B * p.tiles[l] * kC * (l == 0 ? 3 : kC) * 9);
+  const size_t wpart_floats = p.wpart_floats;
 
   const int d = p.h[RN_CONV_LAYERS];
   {

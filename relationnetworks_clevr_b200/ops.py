@@ -227,7 +227,7 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 REL_FLAG_FWD_2PASS = 1
 REL_FLAG_DGRAD_2PASS = 2
 relation_flags = int(os.environ.get("RN_B200_REL_FLAGS", "0"))
-# rn_conv_cfg.flags (RN_CONV_FLAG_*): 1 = fp32 SIMT convolutions instead of the tensor-core ones (tests, A/B timing)
+# rn_conv_cfg.flags (RN_CONV_FLAG_*): 1 = fp32 SIMT convolutions everywhere, 2 = tensor-core forward as well (tests, A/B timing)
 conv_flags = int(os.environ.get("RN_B200_CONV_FLAGS", "0"))
 
 

@@ -291,11 +291,16 @@ def _conv_params(seed):
     return {k_: v for k_, v in p.items() if k_.startswith("conv.")}
 
 
-# side % 64 == 0 runs the tensor-core convolutions (TF32 x3 split), other sides the fp32 SIMT kernels; batches that are
-# not multiples of the images-per-block of the 8x8 / 4x4 layers (4 forward, 2 weight gradient) exercise the image masks
+# side % 64 == 0 runs the tensor-core convolutions (TF32 x3 split: backward by default, flags = 2: forward too), other
+# sides the fp32 SIMT kernels; batches that are not multiples of the images-per-block of the 8x8 / 4x4 layers (4 forward,
+# 2 weight gradient) exercise the image masks
 @pytest.mark.parametrize("B,side", [(3, 32), (2, 64), (5, 64), (2, 128), (5, 128), (1, 192), (1, 256)])
 @pytest.mark.parametrize("training", [True, False])
-def test_conv_objects_match_oracle(B, side, training):
+@pytest.mark.parametrize("flags", [0, 2])
+def test_conv_objects_match_oracle(B, side, training, flags, monkeypatch):
+    if flags and side % 64:
+        pytest.skip("the tensor-core kernels need side % 64 == 0")
+    monkeypatch.setattr(ops, "conv_flags", flags)
     p = _conv_params(side + B)
     img = O.uniform_images(B, side, seed=side)
     d = side // 16
@@ -357,7 +362,7 @@ def test_conv_tensor_core_matches_simt(B, side):
     res = []
     saved_flags = ops.conv_flags
     try:
-        for flags in (0, 1):
+        for flags in (2, 0, 1):          # tensor-core forward + backward, default (backward only), SIMT
             ops.conv_flags = flags
             m = R.ConvInputModel()
             m.load_state_dict({k_[len("conv."):]: v for k_, v in p.items()}, strict=False)
@@ -368,12 +373,14 @@ def test_conv_tensor_core_matches_simt(B, side):
                         **{n: b_.clone() for n, b_ in m.named_buffers() if "running" in n}})
     finally:
         ops.conv_flags = saved_flags
-    for name in res[0]:
-        a, b_ = res[0][name], res[1][name]
-        if float(b_.abs().max()) == 0.0:
-            assert float(a.abs().max()) == 0.0, name
-            continue
-        assert O.rel_err(a.cpu(), b_.cpu()) < (1e-5 if name == "obj" or "running" in name else 1e-4), name
+    for r in res[:2]:
+        for name in r:
+            a, b_ = r[name], res[2][name]
+            if float(b_.abs().max()) == 0.0:
+                assert float(a.abs().max()) == 0.0, name
+                continue
+            assert O.rel_err(a.cpu(), b_.cpu()) < (1e-5 if name == "obj" or "running" in name else 1e-4), name
+    assert torch.equal(res[1]["obj"], res[2]["obj"])       # the default forward IS the fp32 SIMT forward
 
 
 @pytest.mark.parametrize("side", [64, 128])
