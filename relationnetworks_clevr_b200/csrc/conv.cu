@@ -855,16 +855,23 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
     objects_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(dobjects, dA, d, total);
     RN_LAUNCH_CHECK("objects_bwd_kernel");
   }
+  int bn_blocks = 0;      // > 0: `bnpart` already holds that many per-block partials of the layer about to be processed
   for (int l = RN_CONV_LAYERS - 1; l >= 0; --l) {
     RN_CHECK_ARG(Gr[l].dw && Gr[l].dbias && Gr[l].dgamma && Gr[l].dbeta, "conv grads of layer %d have a NULL pointer", l);
     const int hin = p.h[l], hout = p.h[l + 1], hw = hout * hout, tx = cdiv(hout, kTile);
     const float* y = saved + p.y_off[l];
     const float* aff = saved + p.aff_off[l];
-    bn_bwd_reduce_kernel<<<dim3(kC, cfg->B), 256, 0, st>>>(y, dA, aff, bnpart, hw);
-    RN_LAUNCH_CHECK("bn_bwd_reduce_kernel");
-    bn_bwd_finalize_kernel<<<1, 32 * kC, 0, st>>>(bnpart, cfg->B, (double)cfg->B * hw, L[l].gamma, aff, coef, Gr[l].dgamma,
+    // BatchNorm-backward sums: a pass over (y, dA) for the last layer and the SIMT path; the tensor-core data gradient
+    // of layer l + 1 has already left them as per-block partials (bn_blocks of them) in `bnpart`
+    if (bn_blocks == 0) {
+      bn_bwd_reduce_kernel<<<dim3(kC, cfg->B), 256, 0, st>>>(y, dA, aff, bnpart, hw);
+      RN_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+      bn_blocks = cfg->B;
+    }
+    bn_bwd_finalize_kernel<<<1, 32 * kC, 0, st>>>(bnpart, bn_blocks, (double)cfg->B * hw, L[l].gamma, aff, coef, Gr[l].dgamma,
                                                  Gr[l].dbeta, Gr[l].dbias, cfg->training);
     RN_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+    bn_blocks = 0;
     // weight gradient: per-block partials, then a fixed-order sum over blocks
     const float* in = l == 0 ? img : saved + p.y_off[l - 1];
     const float* in_aff = l == 0 ? nullptr : saved + p.aff_off[l - 1];
@@ -932,12 +939,13 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
         if (g.tw == 16) {
           const size_t smem = ctc::DgCfg<16>::SMEM;
           RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          ctc::conv_dgrad_tc_kernel<16><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+          ctc::conv_dgrad_tc_kernel<16><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, saved + p.y_off[l - 1], saved + p.aff_off[l - 1], bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
         } else {
           const size_t smem = ctc::DgCfg<8>::SMEM;
           RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          ctc::conv_dgrad_tc_kernel<8><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+          ctc::conv_dgrad_tc_kernel<8><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, saved + p.y_off[l - 1], saved + p.aff_off[l - 1], bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
         }
+        bn_blocks = g.grid;
       } else {
         conv_dgrad_kernel<<<dim3(qt * qt, cfg->B), 256, 0, st>>>(y, dA, aff, coef, L[l].w, dA_next, hin, hout, qt);
       }

@@ -769,24 +769,33 @@ struct DgCfg {
   static constexpr int RS = TW == 16 ? 20 : 12;
   static constexpr int IS = NR * RS;
   static constexpr int PS = pad32(NIMG * IS, 8);
-  static constexpr size_t SMEM = (size_t)(kC * PS + 2 * kC * kC * 9 + 8 * kC) * sizeof(float);
+  static constexpr size_t SMEM = (size_t)(kC * PS + 2 * kC * kC * 9 + 8 * kC + 4 * kC + 8 * 2 * kC) * sizeof(float);
 };
 
+// y_in / aff_in / bn_part: the raw output and BatchNorm block of the PRODUCING layer (the one whose dA this kernel writes).
+// Its BatchNorm-backward sums  sum g, sum g * xhat  (g = dA where relu(bn(y)) > 0) are taken from the accumulators in the
+// epilogue -- one partial [24][2] per block -- instead of a separate pass that re-reads dA and y_in (bn_bwd_reduce_kernel:
+// 93 us for the first layer at batch 640).
 template <int TW>
 __global__ void __launch_bounds__(256, 2)
 conv_dgrad_tc_kernel(const float* __restrict__ yout, const float* __restrict__ dAout, const float* __restrict__ aff_out,
-                     const float* __restrict__ coef, const float* __restrict__ w, float* __restrict__ dA, int B, int hin,
-                     int hout, int tiles_x, int tiles, int units) {
+                     const float* __restrict__ coef, const float* __restrict__ w, float* __restrict__ dA,
+                     const float* __restrict__ y_in, const float* __restrict__ aff_in, float* __restrict__ bn_part, int B,
+                     int hin, int hout, int tiles_x, int tiles, int units) {
   using D = DgCfg<TW>;
   constexpr int PS = D::PS, IS = D::IS, RS = D::RS, NR = D::NR;
   extern __shared__ __align__(16) float dg_smem[];
   float* dys = dg_smem;                                        // [24][PS]
   float4* wsm = reinterpret_cast<float4*>(dg_smem + kC * PS);  // [tap][ks][nt][lane] (b0 hi, b1 hi, b0 lo, b1 lo)
   float* bnc = dg_smem + kC * PS + 2 * kC * kC * 9;
+  float* affi = bnc + 8 * kC;                                  // (mean, rstd, scale, shift) x 24 of the producing layer
+  float* bnred = affi + 4 * kC;                                // [8 warps][24][2]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int hin2 = hin * hin, hw = hout * hout;
   load_bnc(bnc, aff_out, coef, tid);
+  if (tid < 4 * kC) affi[tid] = aff_in[tid];
+  for (int i = tid; i < 8 * 2 * kC; i += 256) bnred[i] = 0.f;
 
   // B[k = co][n = ci] of (tap, ks, nt): b0 = W[8ks + t][8nt + g][tap], b1 = W[8ks + t + 4][8nt + g][tap]
   for (int idx = tid; idx < 9 * 3 * 3 * 32; idx += 256) {
@@ -887,23 +896,59 @@ conv_dgrad_tc_kernel(const float* __restrict__ yout, const float* __restrict__ d
         }
       }
 
+      float bs[3][2][2];                     // this m-tile's (sum g, sum g * xhat) of channels 8nt + 2t + e
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) bs[nt][0][0] = bs[nt][0][1] = bs[nt][1][0] = bs[nt][1][1] = 0.f;
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         int b, qi, qj;
         if (TW == 16) { b = up.b0; qi = up.r0 + 2 * warp + j; qj = up.c0 + 8 * s + g; }
         else { b = up.b0 + (warp >> 1); qi = (warp & 1) * 4 + 2 * j + s; qj = g; }
         if (b < B && 2 * qi < hin && 2 * qj < hin) {
-          float* o = dA + ((size_t)b * kC + 2 * t) * hin2 + (2 * qi) * hin + 2 * qj;
+          const size_t off = ((size_t)b * kC + 2 * t) * hin2 + (2 * qi) * hin + 2 * qj;
+          float* o = dA + off;
+          const float* yi = y_in + off;
 #pragma unroll
           for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              *reinterpret_cast<float2*>(o + (8 * nt + e) * hin2) = make_float2(acc[0][nt][2 * s + e], acc[1][nt][2 * s + e]);
-              *reinterpret_cast<float2*>(o + (8 * nt + e) * hin2 + hin) = make_float2(acc[2][nt][2 * s + e], acc[3][nt][2 * s + e]);
+              const float2 d0 = make_float2(acc[0][nt][2 * s + e], acc[1][nt][2 * s + e]);
+              const float2 d1 = make_float2(acc[2][nt][2 * s + e], acc[3][nt][2 * s + e]);
+              *reinterpret_cast<float2*>(o + (8 * nt + e) * hin2) = d0;
+              *reinterpret_cast<float2*>(o + (8 * nt + e) * hin2 + hin) = d1;
+              const float2 y0 = *reinterpret_cast<const float2*>(yi + (8 * nt + e) * hin2);
+              const float2 y1 = *reinterpret_cast<const float2*>(yi + (8 * nt + e) * hin2 + hin);
+              const int c = 8 * nt + 2 * t + e;
+              const float mean = affi[c], rstd = affi[kC + c], sc = affi[2 * kC + c], sh = affi[3 * kC + c];
+              const float g0 = fmaf(sc, y0.x, sh) > 0.f ? d0.x : 0.f, g1 = fmaf(sc, y0.y, sh) > 0.f ? d0.y : 0.f;
+              const float g2 = fmaf(sc, y1.x, sh) > 0.f ? d1.x : 0.f, g3 = fmaf(sc, y1.y, sh) > 0.f ? d1.y : 0.f;
+              bs[nt][e][0] += (g0 + g1) + (g2 + g3);
+              bs[nt][e][1] += ((g0 * (y0.x - mean) + g1 * (y0.y - mean)) + (g2 * (y1.x - mean) + g3 * (y1.y - mean))) * rstd;
             }
         }
       }
+      // over the 8 quad lanes (g) that share a channel, then into this warp's row of the block partial
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            float v = bs[nt][e][k];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g == 0) bnred[(warp * kC + 8 * nt + 2 * t + e) * 2 + k] += v;
+          }
     }
+  }
+
+  __syncthreads();
+  if (tid < 2 * kC) {                        // fixed-order sum over the warps: one partial per block
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) v += bnred[wv * 2 * kC + tid];
+    bn_part[(size_t)blockIdx.x * 2 * kC + tid] = v;
   }
 }
 

@@ -100,24 +100,22 @@ extern "C" int rn_f_bwd(const rn_f_cfg* cfg, const float* dlogp, const float* lo
   log_softmax_bwd_rows_kernel<<<cdiv(B, 4), 128, 0, st>>>(dlogp, logp, dz3, B, cfg->A);
   RN_LAUNCH_CHECK("log_softmax_bwd_rows_kernel");
   GemmEpilogue none;
-  // fc3
-  RN_TRY(sgemm(true, false, cfg->A, cfg->F2, B, dz3, cfg->A, h2, cfg->F2, dw3, cfg->F2, none, st));
-  RN_TRY(colsum(dz3, db3, cfg->A, 1, 1, 0, 0, 1, B, st));
-  GemmEpilogue m2;      // through ReLU and dropout: h2 > 0 implies the unit was kept
+  // data path: dz3 -> dz2 (through ReLU and dropout: h2 > 0 implies the unit was kept) -> dz1 -> dxg
+  GemmEpilogue m2;
   m2.mask = h2;
   m2.ldmask = cfg->F2;
   m2.alpha = drop_mask ? cfg->keep_scale : 1.f;
   RN_TRY(sgemm(false, false, B, cfg->F2, cfg->A, dz3, cfg->A, w3, cfg->F2, dz2, cfg->F2, m2, st));
-  // fc2
-  RN_TRY(sgemm(true, false, cfg->F2, cfg->F1, B, dz2, cfg->F2, h1, cfg->F1, dw2, cfg->F1, none, st));
-  RN_TRY(colsum(dz2, db2, cfg->F2, 1, 1, 0, 0, 1, B, st));
   GemmEpilogue m1;
   m1.mask = h1;
   m1.ldmask = cfg->F1;
   RN_TRY(sgemm(false, false, B, cfg->F1, cfg->F2, dz2, cfg->F2, w2, cfg->F1, dz1, cfg->F1, m1, st));
-  // fc1
-  RN_TRY(sgemm(true, false, cfg->F1, cfg->G, B, dz1, cfg->F1, xg, cfg->G, dw1, cfg->G, none, st));
-  RN_TRY(colsum(dz1, db1, cfg->F1, 1, 1, 0, 0, 1, B, st));
   RN_TRY(sgemm(false, false, B, cfg->G, cfg->F1, dz1, cfg->F1, w1, cfg->G, dxg, cfg->G, none, st));
+  // the three weight gradients dW = dz^T h and the three bias gradients (column sums of dz) in ONE launch
+  AtbBuilder wg;
+  wg.add(dz3, cfg->A, h2, cfg->F2, dw3, cfg->F2, cfg->A, cfg->F2, db3);
+  wg.add(dz2, cfg->F2, h1, cfg->F1, dw2, cfg->F1, cfg->F2, cfg->F1, db2);
+  wg.add(dz1, cfg->F1, xg, cfg->G, dw1, cfg->G, cfg->F1, cfg->G, db1);
+  RN_TRY(wg.launch(B, st));
   return RN_OK;
 }

@@ -152,7 +152,9 @@ int relation_qinj_bwd(const RelShape& s, int l, const float* q, const float* con
   const int off = (l == 0 ? 2 * s.k : s.G);
   GemmEpilogue none;
   // dWq[o, j] = sum_b delta[b,o] q[b,j]
-  RN_TRY(sgemm(true, false, s.G, s.Q, s.B, delta, s.G, q, s.Q, dg_w[l] + off, fan, none, st));
+  AtbBuilder wg;
+  wg.add(delta, s.G, q, s.Q, dg_w[l] + off, fan, s.G, s.Q, nullptr);
+  RN_TRY(wg.launch(s.B, st));
   // dq[b, j] = sum_o delta[b,o] Wq[o,j]
   RN_TRY(sgemm(false, false, s.B, s.Q, s.G, delta, s.G, g_w[l] + off, fan, dq, s.Q, none, st));
   return RN_OK;

@@ -239,6 +239,111 @@ inline int sgemm(bool at, bool bt, int M, int N, int K, const float* A, long lon
   return RN_OK;
 }
 
+// ---- grouped small weight-gradient products ------------------------------------------------------------------
+// C_p[M_p x N_p] = A_p^T B_p  (A_p [K x M_p], B_p [K x N_p], K = batch rows) for up to four problems in ONE launch, plus
+// the column sums of A_p (bias gradients).  These are the f-MLP / question-injection weight gradients: 256 x 256 outputs
+// over K = batch, which as 64x64-tile GEMMs put 16 blocks on the machine for 54 us each.  Here a block owns one 32x32
+// output tile for the whole K (no split-K workspace, fixed summation order: deterministic), so the three f-MLP
+// gradients are 136 blocks = one wave.  Thread (ty, tx) of 16 x 16 owns rows 2ty, 2ty+1 and columns 2tx, 2tx+1.
+struct AtbProblem {
+  const float* A;
+  const float* B;
+  float* C;
+  float* colsum;      // [M] column sums of A, or nullptr
+  int lda, ldb, ldc, M, N;
+  int tile_begin;     // first block of this problem
+};
+struct AtbGroup {
+  AtbProblem p[4];
+  int count;
+};
+
+static __global__ void __launch_bounds__(256) atb_group_kernel(AtbGroup g, int K) {
+  __shared__ __align__(16) float As[2][32][36], Bs[2][32][36];
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < g.count && (int)blockIdx.x >= g.p[i].tile_begin) pi = i;
+  const AtbProblem& P = g.p[pi];
+  const int tiles_n = (P.N + 31) / 32;
+  const int tile = blockIdx.x - P.tile_begin;
+  const int m0 = (tile / tiles_n) * 32, n0 = (tile % tiles_n) * 32;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lr = tid >> 3, lc = (tid & 7) * 4;          // staging: row k = lr, columns lc .. lc + 3
+  const bool a_vec = (P.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(P.A) & 15u) == 0 && m0 + 32 <= P.M;
+  const bool b_vec = (P.ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(P.B) & 15u) == 0 && n0 + 32 <= P.N;
+
+  auto load = [&](const float* X, int ld, int lim, int c0, bool vec, int k) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < K) {
+      const float* r = X + (long long)k * ld + c0 + lc;
+      if (vec) v = *reinterpret_cast<const float4*>(r);
+      else {
+        if (c0 + lc < lim) v.x = r[0];
+        if (c0 + lc + 1 < lim) v.y = r[1];
+        if (c0 + lc + 2 < lim) v.z = r[2];
+        if (c0 + lc + 3 < lim) v.w = r[3];
+      }
+    }
+    return v;
+  };
+
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float cs0 = 0.f, cs1 = 0.f;
+  float4 ra = load(P.A, P.lda, P.M, m0, a_vec, lr), rb = load(P.B, P.ldb, P.N, n0, b_vec, lr);
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    *reinterpret_cast<float4*>(&As[buf][lr][lc]) = ra;
+    *reinterpret_cast<float4*>(&Bs[buf][lr][lc]) = rb;
+    __syncthreads();
+    if (k0 + 32 < K) {
+      ra = load(P.A, P.lda, P.M, m0, a_vec, k0 + 32 + lr);
+      rb = load(P.B, P.ldb, P.N, n0, b_vec, k0 + 32 + lr);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float2 a = *reinterpret_cast<const float2*>(&As[buf][k][2 * ty]);
+      const float2 b = *reinterpret_cast<const float2*>(&Bs[buf][k][2 * tx]);
+      acc[0][0] = fmaf(a.x, b.x, acc[0][0]);
+      acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+      acc[1][0] = fmaf(a.y, b.x, acc[1][0]);
+      acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+      cs0 += a.x;
+      cs1 += a.y;
+    }
+    buf ^= 1;      // the next store goes to the other buffer: one barrier per chunk
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int gm = m0 + 2 * ty + i, gn = n0 + 2 * tx + j;
+      if (gm < P.M && gn < P.N) P.C[(long long)gm * P.ldc + gn] = acc[i][j];
+    }
+  if (P.colsum != nullptr && n0 == 0 && tx == 0) {
+    if (m0 + 2 * ty < P.M) P.colsum[m0 + 2 * ty] = cs0;
+    if (m0 + 2 * ty + 1 < P.M) P.colsum[m0 + 2 * ty + 1] = cs1;
+  }
+}
+
+struct AtbBuilder {
+  AtbGroup g;
+  int tiles = 0;
+  AtbBuilder() { g.count = 0; }
+  void add(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, float* colsum_out) {
+    AtbProblem& p = g.p[g.count++];
+    p.A = A; p.B = B; p.C = C; p.colsum = colsum_out;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.M = M; p.N = N;
+    p.tile_begin = tiles;
+    tiles += cdiv(M, 32) * cdiv(N, 32);
+  }
+  int launch(int K, cudaStream_t st) {
+    atb_group_kernel<<<tiles, 256, 0, st>>>(g, K);
+    RN_LAUNCH_CHECK("atb_group_kernel");
+    return RN_OK;
+  }
+};
+
 // ---- strided column sums -----------------------------------------------------------------
 // out[(g1*n2 + g2), :] = sum_{i<count} A[(g1*s1 + g2*s2 + i*si), :]   (rows of width N, ld = N)
 static __global__ void colsum_kernel(const float* __restrict__ A, float* __restrict__ out, int N, int n2, long long s1,
