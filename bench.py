@@ -460,7 +460,8 @@ def run_ours(args):
         precision = strong["precision"]
         dtype = {"fp32": "f32 (SIMT)",
                  "parity": "f16 operands / f32 accumulate: forward 3 MMA passes (A_hi W_hi + A_lo W_hi + A_hi W_lo), "
-                           "data gradient 1 pass (W_hi), weight gradient 1 pass; layer 0, conv, LSTM, f-MLP, Adam in f32",
+                           "data gradient 1 pass (W_hi), weight gradient 1 pass; conv backward TF32 operands x 3 passes (hi/lo split, "
+                           "f32-level), f32 accumulate; layer 0, conv forward, LSTM, f-MLP, Adam in f32",
                  "fast": "f16 operands / f32 accumulate, 1 MMA pass everywhere"}[precision]
         line = {
             "metric": "questions/sec", "value": value, "unit": "questions/s", "n_gpus": world, "steps": args.steps,

@@ -18,13 +18,16 @@ KEEP = ("gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed")
 
 
-def launches(path):
-    rows = list(csv.reader(open(path)))
+def launches(path, steps=1):
+    rows = list(csv.reader(open(path, errors="ignore")))
     hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
     hdr = rows[hi]
     kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
     agg = collections.OrderedDict()
-    for r in rows[hi + 1:]:
+    body = [r for r in rows[hi + 1:] if len(r) > mv]
+    if steps > 1:                       # the capture holds `steps` identical steps: keep the last one
+        body = body[len(body) - len(body) // steps:]
+    for r in body:
         if len(r) <= mv:
             continue
         a = agg.setdefault(r[kn][:90], [0, 0.0])
@@ -46,6 +49,10 @@ def full(path):
             if h in KEEP:
                 print(f"   {h:85s} {units[i]:12s} {r[i]}")
 
+
+if __name__ == "__main__" and sys.argv[1] == "laststep":
+    launches(sys.argv[2], int(sys.argv[3]))
+    sys.exit(0)
 
 if __name__ == "__main__":
     {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])

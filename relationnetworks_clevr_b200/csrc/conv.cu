@@ -693,7 +693,7 @@ struct TcGrid {
   int tw, tiles_x, tiles, units, grid;
 };
 // fwd / dgrad: unit = TW x TW outputs (quads); wgrad: 8 x 16 outputs (TW = 16) or two 8x8 images
-static TcGrid tc_grid(int B, int hout, int unit_rows16, int nimg8) {
+static TcGrid tc_grid(int B, int hout, int unit_rows16, int nimg8, int blocks_per_sm = 2) {
   TcGrid g;
   g.tw = hout <= 8 ? 8 : 16;
   if (g.tw == 16) {
@@ -705,7 +705,7 @@ static TcGrid tc_grid(int B, int hout, int unit_rows16, int nimg8) {
     g.tiles = 1;
     g.units = cdiv(B, nimg8);
   }
-  const int slots = 2 * sm_count();
+  const int slots = blocks_per_sm * sm_count();
   const int per = cdiv(g.units, slots);
   g.grid = cdiv(g.units, per);
   return g;
@@ -880,24 +880,31 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
     const bool tc = conv_tc_ok(*cfg);
     int nblk = p.tiles[l] * cfg->B;
     if (tc && l == 0) {
-      const TcGrid g = tc_grid(cfg->B, hout, 16, 1);
+      // single-stage form, two blocks per SM: the per-unit MMA work of the RGB layer is too small for the producer /
+      // consumer ring to pay (measured 0.20 ms against 0.28 ms warp-specialised at batch 640)
+      const TcGrid g = tc_grid(cfg->B, hout, 16, 1, 2);
       nblk = g.grid;
-      const size_t smem = ctc::Wg3Cfg::SMEM;
-      if (cfg->img_u8)
-        ctc::conv_wgrad3_tc_kernel<true><<<g.grid, 256, smem, st>>>(in, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
-      else
-        ctc::conv_wgrad3_tc_kernel<false><<<g.grid, 256, smem, st>>>(in, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
-    } else if (tc) {
-      const TcGrid g = tc_grid(cfg->B, hout, 8, 2);
-      nblk = g.grid;
-      if (g.tw == 16) {
-        const size_t smem = ctc::WgCfg<16>::SMEM;
-        RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctc::conv_wgrad_tc_kernel<16><<<g.grid, 224, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+      const size_t smem = ctc::Wg3Cfg::smem(false);
+      if (cfg->img_u8) {
+        RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad3_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctc::conv_wgrad3_tc_kernel<true, false><<<g.grid, 256, smem, st>>>(in, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
       } else {
-        const size_t smem = ctc::WgCfg<8>::SMEM;
-        RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctc::conv_wgrad_tc_kernel<8><<<g.grid, 224, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+        RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctc::conv_wgrad3_tc_kernel<false, false><<<g.grid, 256, smem, st>>>(in, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+      }
+    } else if (tc) {
+      if (hout > 8) {
+        const TcGrid g = tc_grid(cfg->B, hout, 8, 2, 1);
+        nblk = g.grid;
+        const size_t smem = ctc::WgCfg<16>::smem(true);
+        RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctc::conv_wgrad_tc_kernel<16, true><<<g.grid, 448, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+      } else {
+        const TcGrid g = tc_grid(cfg->B, hout, 8, 2, 2);
+        nblk = g.grid;
+        const size_t smem = ctc::WgCfg<8>::smem(false);
+        RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctc::conv_wgrad_tc_kernel<8, false><<<g.grid, 224, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
       }
     } else if (l == 0 && cfg->img_u8) {
       const size_t smem = wgrad_smem_bytes<3>();
@@ -935,15 +942,15 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
       const int qt = cdiv(hout, kTile);
       // reads (y_l, dA_l), writes dA_{l-1} into the other buffer
       if (tc) {
-        const TcGrid g = tc_grid(cfg->B, hout, 16, 4);
+        const TcGrid g = tc_grid(cfg->B, hout, 16, 4, hout > 8 ? 1 : 2);
         if (g.tw == 16) {
-          const size_t smem = ctc::DgCfg<16>::SMEM;
-          RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          ctc::conv_dgrad_tc_kernel<16><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, saved + p.y_off[l - 1], saved + p.aff_off[l - 1], bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+          const size_t smem = ctc::DgCfg<16>::smem(true);
+          RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          ctc::conv_dgrad_tc_kernel<16, true><<<g.grid, 512, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, saved + p.y_off[l - 1], saved + p.aff_off[l - 1], bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
         } else {
-          const size_t smem = ctc::DgCfg<8>::SMEM;
-          RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          ctc::conv_dgrad_tc_kernel<8><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, saved + p.y_off[l - 1], saved + p.aff_off[l - 1], bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+          const size_t smem = ctc::DgCfg<8>::smem(false);
+          RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          ctc::conv_dgrad_tc_kernel<8, false><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, saved + p.y_off[l - 1], saved + p.aff_off[l - 1], bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
         }
         bn_blocks = g.grid;
       } else {

@@ -481,10 +481,52 @@ __device__ __forceinline__ void load_bnc(float* __restrict__ bnc, const float* _
 }
 
 // ------------------------------------------------------------------------------------------
+// Warp specialisation (WS = true) of the three backward kernels.  In the first version every warp alternated between
+// staging (global loads, BatchNorm transform, shared-memory stores) and MMAs, and the two resident blocks of an SM drifted
+// into phase: the tensor pipe idled ~60 % of the time (ncu: pipe_tensor 25 - 42 %).  Here a block has as many PRODUCER
+// warps as consumer warps: producers stage unit i + 1 into the other half of a two-stage ring while the consumers
+// multiply unit i; the hand-off is a pair of named barriers per stage (bar.arrive by one role, bar.sync by the other --
+// full[s] = 1 + s, empty[s] = 3 + s), which also order the shared-memory traffic.  WS = false keeps the single-stage
+// all-roles form (the 8x8 layer, whose units are too few to fill a ring).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Runs the unit loop of one block: stage(s, pos) by the producers, compute(s, pos) by the consumers.
+template <bool WS, int NROLE, typename Walk, typename Stage, typename Compute>
+__device__ __forceinline__ void unit_loop(int units, Walk walk, Stage&& stage, Compute&& compute) {
+  const int n_my = (int)blockIdx.x < units ? (units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (WS) {
+    if ((int)threadIdx.x >= NROLE) {
+      for (int i = 0; i < n_my; ++i, walk.next()) {
+        const int s = i & 1;
+        if (i >= 2) bar_sync(3 + s, 2 * NROLE);          // the consumers have released this stage
+        stage(s, walk.pos());
+        bar_arrive(1 + s, 2 * NROLE);
+      }
+    } else {
+      for (int i = 0; i < n_my; ++i, walk.next()) {
+        const int s = i & 1;
+        bar_sync(1 + s, 2 * NROLE);
+        compute(s, walk.pos());
+        if (i + 2 < n_my) bar_arrive(3 + s, 2 * NROLE);
+      }
+    }
+  } else {
+    for (int i = 0; i < n_my; ++i, walk.next()) {
+      __syncthreads();                         // the previous unit's fragments have been read
+      stage(0, walk.pos());
+      __syncthreads();
+      compute(0, walk.pos());
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // weight gradient of the 24 -> 24 layers: dW[co][ci][tap] = sum_pixels dy[co][p] * act(in)[ci][tap(p)].
 // GEMM  D[(tap, ci)][co] = sum_p A[(tap, ci)][p] * B[p][co]:  M = 216 = 27 row groups (8 channels of one tap) paired into
 // 14 m-tiles (the 28th group is a dummy), N = 24 = 3 n-tiles, K = 8 consecutive output pixels of one row per MMA.
-// Block = 7 warps, warp w owns m-tiles 2w, 2w+1 (24 accumulators) for ALL pixels; persistent over units of 128 output
+// 7 consumer warps, warp w owns m-tiles 2w, 2w+1 (24 accumulators) for ALL pixels; persistent over units of 128 output
 // pixels (TW = 16: 8 rows x 16 columns of one image, TW = 8: the 8x8 outputs of two images); the accumulators live in
 // registers across units, one partial [24][24][9] per block, summed by a fixed-order reduction afterwards.
 // ------------------------------------------------------------------------------------------
@@ -496,11 +538,12 @@ struct WgCfg {
   static constexpr int IS = NR * Geo<TW>::RS;
   static constexpr int PS = pad32(NIMG * IS, 4);
   static constexpr int LD = 132;                                     // dy: [24][128 pixels + 4]
-  static constexpr size_t SMEM = (size_t)(kC * PS + kC * LD + 2 * kC + 8 * kC) * sizeof(float);
+  static constexpr int STAGE = kC * PS + kC * LD;                    // floats per ring stage
+  static constexpr size_t smem(bool ws) { return (size_t)((ws ? 2 : 1) * STAGE + 2 * kC + 8 * kC) * sizeof(float); }
 };
 
-template <int TW>
-__global__ void __launch_bounds__(224, 2)
+template <int TW, bool WS>
+__global__ void __launch_bounds__(WS ? 448 : 224, WS ? 1 : 2)
 conv_wgrad_tc_kernel(const float* __restrict__ in, const float* __restrict__ in_aff, const float* __restrict__ yout,
                      const float* __restrict__ dA, const float* __restrict__ aff_out, const float* __restrict__ coef,
                      float* __restrict__ part, int B, int hin, int hout, int tiles_x, int tiles, int units) {
@@ -508,15 +551,16 @@ conv_wgrad_tc_kernel(const float* __restrict__ in, const float* __restrict__ in_
   using G = Geo<TW>;
   constexpr int PS = W::PS, IS = W::IS, RS = G::RS, LD = W::LD, NT = W::NT;
   extern __shared__ __align__(16) float wg_tc_smem[];
-  float* patch = wg_tc_smem;                 // [24][PS]
-  float* dys = patch + kC * PS;              // [24][LD]
-  float* affs = dys + kC * LD;               // scale[24], shift[24] of the producing layer
-  float* bnc = affs + 2 * kC;                // [24][8]
+  float* ring = wg_tc_smem;                                // [stages][patch [24][PS] | dy [24][LD]]
+  float* affs = ring + (WS ? 2 : 1) * W::STAGE;            // scale[24], shift[24] of the producing layer
+  float* bnc = affs + 2 * kC;                              // [24][8]
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int tid = WS && threadIdx.x >= NT ? threadIdx.x - NT : threadIdx.x;      // index within the role
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int hin2 = hin * hin, hw = hout * hout;
-  if (tid < 2 * kC) affs[tid] = in_aff[2 * kC + tid];
-  load_bnc(bnc, aff_out, coef, tid);
+  if (threadIdx.x < 2 * kC) affs[threadIdx.x] = in_aff[2 * kC + threadIdx.x];
+  load_bnc(bnc, aff_out, coef, threadIdx.x);
+  __syncthreads();
 
   // A rows: m-tile mt, half h (fragment rows g / g + 8) = row group q = 4*warp + 2*mt + h = chunk*9 + tap
   int arow[2][2];
@@ -537,56 +581,63 @@ conv_wgrad_tc_kernel(const float* __restrict__ in, const float* __restrict__ in_
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
 
-  UnitWalk<W::NIMG, 8, 16> walk(tiles, tiles_x);
-  for (int u = blockIdx.x; u < units; u += gridDim.x, walk.next()) {
-    const UnitPos up = walk.pos();
-    __syncthreads();                         // the previous unit's fragments have been read (and affs / bnc are visible)
-    // input patch in two passes (bounds the registers of the staging): TW = 16: rows 0..8 / 9..16 of all 24 channels
-    // (thread -> one channel plane and vector column, walking down the rows), TW = 8: channels 0..11 / 12..23
-    if (TW == 16) {
-      const float* inb = in + (size_t)up.b0 * kC * hin2;
-      {
-        PatchStager<TW, 1, kC, 9, PS, IS, NT, false> stg;
-        stg.issue(inb, 1, kC * hin2, hin2, 2 * up.r0 - 1, 2 * up.c0 - 1, hin, tid);
-        stg.commit(patch, affs, tid);
-      }
-      {
-        PatchStager<TW, 1, kC, 8, PS, IS, NT, false> stg;
-        stg.issue(inb, 1, kC * hin2, hin2, 2 * up.r0 - 1 + 9, 2 * up.c0 - 1, hin, tid);
-        stg.commit(patch + 9 * RS, affs, tid);
-      }
-    } else {
-#pragma unroll 1
-      for (int c0 = 0; c0 < kC; c0 += 12) {
-        PatchStager<TW, W::NIMG, 12, W::NR, PS, IS, NT, false> stg;
-        stg.issue(in + ((size_t)up.b0 * kC + c0) * hin2, B - up.b0, kC * hin2, hin2, 2 * up.r0 - 1, 2 * up.c0 - 1, hin, tid);
-        stg.commit(patch + c0 * PS, affs + c0, tid);
-      }
-    }
+  auto stage = [&](int s, const UnitPos& up) {
+    float* patch = ring + s * W::STAGE;
+    float* dys = patch + kC * PS;
     // dy: 24 channels x 128 pixels; lane -> 4 pixels of a row (fixed), warp -> channels w, w + 7, ..
-    {
-      const int px = lane * 4;
-      int b, oy, ox;
-      if (TW == 16) { b = up.b0; oy = up.r0 + (px >> 4); ox = up.c0 + (px & 15); }
-      else { b = up.b0 + (px >> 6); oy = (px >> 3) & 7; ox = px & 7; }
-      const bool pv = b < B && oy < hout && ox < hout;
-      const size_t off = (size_t)b * kC * hw + oy * hout + ox;
+    const int px = lane * 4;
+    int b, oy, ox;
+    if (TW == 16) { b = up.b0; oy = up.r0 + (px >> 4); ox = up.c0 + (px & 15); }
+    else { b = up.b0 + (px >> 6); oy = (px >> 3) & 7; ox = px & 7; }
+    const bool pv = b < B && oy < hout && ox < hout;
+    const size_t off = pv ? (size_t)b * kC * hw + oy * hout + ox : 0;
+    auto stage_dy = [&](const float4 (&yv)[4], const float4 (&dav)[4]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int co = warp + 7 * i;
         if (co < kC) {
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (pv) {
-            BnBwdCoef k;
-            k.load(bnc, co);
-            o = k.apply4(*reinterpret_cast<const float4*>(yout + off + co * hw), *reinterpret_cast<const float4*>(dA + off + co * hw));
-          }
-          *reinterpret_cast<float4*>(dys + co * LD + px) = o;
+          BnBwdCoef k;
+          k.load(bnc, co);
+          *reinterpret_cast<float4*>(dys + co * LD + px) = pv ? k.apply4(yv[i], dav[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+    };
+    float4 yv[4], dav[4];
+    auto load_dy = [&]() {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int co = warp + 7 * i < kC ? warp + 7 * i : 0;
+        yv[i] = *reinterpret_cast<const float4*>(yout + off + co * hw);
+        dav[i] = *reinterpret_cast<const float4*>(dA + off + co * hw);
+      }
+    };
+    if (TW == 16) {
+      // ALL of the unit's loads in flight at once (one memory round trip per unit): rows 0..8 / 9..16 of the 24 input
+      // planes (thread -> one plane and vector column, walking down the rows) and the (y, dA) vectors of dy
+      const float* inb = in + (size_t)up.b0 * kC * hin2;
+      PatchStager<TW, 1, kC, 9, PS, IS, NT, false> s1;
+      PatchStager<TW, 1, kC, 8, PS, IS, NT, false> s2;
+      s1.issue(inb, 1, kC * hin2, hin2, 2 * up.r0 - 1, 2 * up.c0 - 1, hin, tid);
+      s2.issue(inb, 1, kC * hin2, hin2, 2 * up.r0 - 1 + 9, 2 * up.c0 - 1, hin, tid);
+      load_dy();
+      s1.commit(patch, affs, tid);
+      s2.commit(patch + 9 * RS, affs, tid);
+      stage_dy(yv, dav);
+    } else {
+      load_dy();
+#pragma unroll 1
+      for (int c0 = 0; c0 < kC; c0 += 12) {       // channels 0..11 / 12..23 (bounds the registers of the staging)
+        PatchStager<TW, W::NIMG, 12, W::NR, PS, IS, NT, false> stg;
+        stg.issue(in + ((size_t)up.b0 * kC + c0) * hin2, B - up.b0, kC * hin2, hin2, 2 * up.r0 - 1, 2 * up.c0 - 1, hin, tid);
+        stg.commit(patch + c0 * PS, affs + c0, tid);
+      }
+      stage_dy(yv, dav);
     }
-    __syncthreads();
+  };
 
+  auto compute = [&](int s, const UnitPos&) {
+    const float* patch = ring + s * W::STAGE;
+    const float* dys = patch + kC * PS;
 #pragma unroll 4
     for (int ks = 0; ks < 16; ++ks) {
       const int poff = TW == 16 ? (2 * (ks >> 1)) * RS + (ks & 1) * 8 : (ks >> 3) * IS + (2 * (ks & 7)) * RS;
@@ -606,8 +657,11 @@ conv_wgrad_tc_kernel(const float* __restrict__ in, const float* __restrict__ in_
         mma3x3(acc[mt], ah, al, bh, bl);
       }
     }
-  }
+  };
 
+  unit_loop<WS, NT>(units, UnitWalk<W::NIMG, 8, 16>(tiles, tiles_x), stage, compute);
+
+  if (WS && threadIdx.x >= NT) return;
   float* out = part + (size_t)blockIdx.x * (kC * kC * 9);
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -627,34 +681,36 @@ conv_wgrad_tc_kernel(const float* __restrict__ in, const float* __restrict__ in_
 // ------------------------------------------------------------------------------------------
 // weight gradient of the RGB layer: dW[co][ci][tap], 24 x 27.  GEMM  D[co][(tap, ci)] = sum_p dy[co][p] * in[(tap, ci)][p]:
 // M = 24 (two m-tiles, the upper half of the second one is zero), N = 27 padded to 32 = 4 n-tiles, K = 8 pixels.
-// The output is tiny, so the PIXELS are split over the warps (warp w: rows 2w, 2w+1 of a 16x16 output tile) and the 8
-// per-warp results are combined by a fixed-order sum at the end of the persistent block.
+// The output is tiny, so the PIXELS are split over the 8 consumer warps (warp w: rows 2w, 2w+1 of a 16x16 output tile) and
+// the 8 per-warp results are combined by a fixed-order sum at the end of the persistent block.
 // ------------------------------------------------------------------------------------------
 struct Wg3Cfg {
   static constexpr int NR = 33;
   static constexpr int PS = pad32(NR * Geo<16>::RS, 4);              // 1188 (== 4 mod 32)
   static constexpr int LD = 260;                                     // dy: [24][256 pixels + 4]
-  static constexpr int RED = 8 * kC * 27;                            // aliases the patch + dy at the end
-  static constexpr int MAIN = 3 * PS + kC * LD;
-  static constexpr size_t SMEM = (size_t)((MAIN > RED ? MAIN : RED) + 8 * kC) * sizeof(float);
+  static constexpr int RED = 8 * kC * 27;                            // aliases stage 0 at the end
+  static constexpr int STAGE = 3 * PS + kC * LD;
+  static constexpr size_t smem(bool ws) { return (size_t)((ws ? 2 : 1) * STAGE + 8 * kC) * sizeof(float); }
+  static_assert(STAGE >= RED, "the final reduction aliases one stage");
 };
 
-template <bool U8>
-__global__ void __launch_bounds__(256, 2)
+template <bool U8, bool WS>
+__global__ void __launch_bounds__(WS ? 512 : 256, WS ? 1 : 2)
 conv_wgrad3_tc_kernel(const void* __restrict__ in, const float* __restrict__ yout, const float* __restrict__ dA,
                       const float* __restrict__ aff_out, const float* __restrict__ coef, float* __restrict__ part, int B,
                       int hin, int hout, int tiles_x, int tiles, int units) {
   using G = Geo<16>;
-  constexpr int PS = Wg3Cfg::PS, RS = G::RS, LD = Wg3Cfg::LD;
+  constexpr int PS = Wg3Cfg::PS, RS = G::RS, LD = Wg3Cfg::LD, NT = 256;
   extern __shared__ __align__(16) float wg3_smem[];
-  float* patch = wg3_smem;                  // [3][PS]
-  float* dys = patch + 3 * PS;              // [24][LD]
+  float* ring = wg3_smem;                   // [stages][patch [3][PS] | dy [24][LD]]
   float* red = wg3_smem;                    // [8][24*27] at the end
-  float* bnc = wg3_smem + (Wg3Cfg::MAIN > Wg3Cfg::RED ? Wg3Cfg::MAIN : Wg3Cfg::RED);
+  float* bnc = wg3_smem + (WS ? 2 : 1) * Wg3Cfg::STAGE;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int tid = WS && threadIdx.x >= NT ? threadIdx.x - NT : threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int hin2 = hin * hin, hw = hout * hout;
-  load_bnc(bnc, aff_out, coef, tid);
+  load_bnc(bnc, aff_out, coef, threadIdx.x);
+  __syncthreads();
 
   int noff[4];                              // B rows: n = 8nt + g = tap*3 + ci
 #pragma unroll
@@ -670,36 +726,36 @@ conv_wgrad3_tc_kernel(const void* __restrict__ in, const float* __restrict__ you
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
 
-  UnitWalk<1, 16, 16> walk(tiles, tiles_x);
-  for (int u = blockIdx.x; u < units; u += gridDim.x, walk.next()) {
-    const UnitPos up = walk.pos();
-    __syncthreads();
-    {
-      PatchStager<16, 1, 3, Wg3Cfg::NR, PS, 0, 256, U8> stg;
-      const size_t base = (size_t)up.b0 * 3 * hin2;
-      const void* inb = U8 ? static_cast<const void*>(static_cast<const unsigned char*>(in) + base)
-                           : static_cast<const void*>(static_cast<const float*>(in) + base);
-      stg.issue(inb, 1, 3 * hin2, hin2, 2 * up.r0 - 1, 2 * up.c0 - 1, hin, tid);
-      // dy of the 16x16 tile while the image loads are in flight: thread -> 4 pixels of a row (fixed), channels tid/64 + 4i
-      const int px = (tid & 63) * 4;
-      const int oy = up.r0 + (px >> 4), ox = up.c0 + (px & 15);
-      const bool pv = oy < hout && ox < hout;
-      const size_t off = (size_t)up.b0 * kC * hw + oy * hout + ox;
+  auto stage = [&](int s, const UnitPos& up) {
+    float* patch = ring + s * Wg3Cfg::STAGE;
+    float* dys = patch + 3 * PS;
+    PatchStager<16, 1, 3, Wg3Cfg::NR, PS, 0, NT, U8> stg;
+    const size_t base = (size_t)up.b0 * 3 * hin2;
+    const void* inb = U8 ? static_cast<const void*>(static_cast<const unsigned char*>(in) + base)
+                         : static_cast<const void*>(static_cast<const float*>(in) + base);
+    stg.issue(inb, 1, 3 * hin2, hin2, 2 * up.r0 - 1, 2 * up.c0 - 1, hin, tid);
+    // dy of the 16x16 tile while the image loads are in flight: thread -> 4 pixels of a row (fixed), channels tid/64 + 4i
+    const int px = (tid & 63) * 4;
+    const int oy = up.r0 + (px >> 4), ox = up.c0 + (px & 15);
+    const bool pv = oy < hout && ox < hout;
+    const size_t off = (size_t)up.b0 * kC * hw + oy * hout + ox;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int co = (tid >> 6) + 4 * i;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pv) {
-          BnBwdCoef k;
-          k.load(bnc, co);
-          o = k.apply4(*reinterpret_cast<const float4*>(yout + off + co * hw), *reinterpret_cast<const float4*>(dA + off + co * hw));
-        }
-        *reinterpret_cast<float4*>(dys + co * LD + px) = o;
+    for (int i = 0; i < 6; ++i) {
+      const int co = (tid >> 6) + 4 * i;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pv) {
+        BnBwdCoef k;
+        k.load(bnc, co);
+        o = k.apply4(*reinterpret_cast<const float4*>(yout + off + co * hw), *reinterpret_cast<const float4*>(dA + off + co * hw));
       }
-      stg.commit(patch, nullptr, tid);
+      *reinterpret_cast<float4*>(dys + co * LD + px) = o;
     }
-    __syncthreads();
+    stg.commit(patch, nullptr, tid);
+  };
 
+  auto compute = [&](int s, const UnitPos&) {
+    const float* patch = ring + s * Wg3Cfg::STAGE;
+    const float* dys = patch + 3 * PS;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       const int row = 2 * warp + (ks >> 1), ox0 = (ks & 1) * 8;
@@ -729,22 +785,26 @@ conv_wgrad3_tc_kernel(const void* __restrict__ in, const float* __restrict__ you
             mma_tf32(acc[mt][nt], a[0], a[1], a[2], a[3], b[0], b[1]);
           }
     }
-  }
+  };
 
+  unit_loop<WS, NT>(units, UnitWalk<1, 16, 16>(tiles, tiles_x), stage, compute);
+
+  __syncthreads();                          // every role is done with the ring: it becomes the reduction buffer
+  if (!WS || threadIdx.x < NT) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int co = 16 * mt + 8 * h + g, n = 8 * nt + 2 * t + e;
+            if (co < kC && n < 27) red[(warp * kC + co) * 27 + n] = acc[mt][nt][2 * h + e];
+          }
+  }
   __syncthreads();
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int co = 16 * mt + 8 * h + g, n = 8 * nt + 2 * t + e;
-          if (co < kC && n < 27) red[(warp * kC + co) * 27 + n] = acc[mt][nt][2 * h + e];
-        }
-  __syncthreads();
-  for (int idx = tid; idx < kC * 27; idx += 256) {
+  for (int idx = threadIdx.x; idx < kC * 27; idx += blockDim.x) {
     float s = 0.f;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) s += red[wv * kC * 27 + idx];
@@ -758,9 +818,9 @@ conv_wgrad3_tc_kernel(const void* __restrict__ in, const float* __restrict__ you
 // data gradient (layers 2..4): dA_prev[ci][ih][iw] = sum_{co, kh, kw} dy[co][oh][ow] W[co][ci][kh][kw], ih = 2 oh + kh - 1.
 // Per parity class (ih & 1, iw & 1) a GEMM  D[quad][ci] = sum_{tap in class, co} dy[co][quad + shift(tap)] * W[co][ci][tap]
 // (1, 2, 2, 4 taps): M = 16 quads (two 8-quad row segments), N = 24, K = 8 output channels of one tap.  The A fragment
-// of a shift (0/1, 0/1) of the dy window is loaded once and feeds every tap that uses it.  Persistent blocks of 256
-// threads; unit = 16x16 quads (32x32 input pixels) of one image (TW = 16) or the 8x8 quads of four images (TW = 8);
-// weight fragments pre-split (hi, lo) in shared memory.
+// of a shift (0/1, 0/1) of the dy window is loaded once and feeds every tap that uses it.  8 consumer warps; unit =
+// 16x16 quads (32x32 input pixels) of one image (TW = 16) or the 8x8 quads of four images (TW = 8); weight fragments
+// pre-split (hi, lo) in shared memory.
 // ------------------------------------------------------------------------------------------
 template <int TW>
 struct DgCfg {
@@ -769,36 +829,40 @@ struct DgCfg {
   static constexpr int RS = TW == 16 ? 20 : 12;
   static constexpr int IS = NR * RS;
   static constexpr int PS = pad32(NIMG * IS, 8);
-  static constexpr size_t SMEM = (size_t)(kC * PS + 2 * kC * kC * 9 + 8 * kC + 4 * kC + 8 * 2 * kC) * sizeof(float);
+  static constexpr int STAGE = kC * PS;
+  static constexpr size_t smem(bool ws) {
+    return (size_t)((ws ? 2 : 1) * STAGE + 2 * kC * kC * 9 + 8 * kC + 4 * kC + 8 * 2 * kC) * sizeof(float);
+  }
 };
 
 // y_in / aff_in / bn_part: the raw output and BatchNorm block of the PRODUCING layer (the one whose dA this kernel writes).
 // Its BatchNorm-backward sums  sum g, sum g * xhat  (g = dA where relu(bn(y)) > 0) are taken from the accumulators in the
 // epilogue -- one partial [24][2] per block -- instead of a separate pass that re-reads dA and y_in (bn_bwd_reduce_kernel:
 // 93 us for the first layer at batch 640).
-template <int TW>
-__global__ void __launch_bounds__(256, 2)
+template <int TW, bool WS>
+__global__ void __launch_bounds__(WS ? 512 : 256, WS ? 1 : 2)
 conv_dgrad_tc_kernel(const float* __restrict__ yout, const float* __restrict__ dAout, const float* __restrict__ aff_out,
                      const float* __restrict__ coef, const float* __restrict__ w, float* __restrict__ dA,
                      const float* __restrict__ y_in, const float* __restrict__ aff_in, float* __restrict__ bn_part, int B,
                      int hin, int hout, int tiles_x, int tiles, int units) {
   using D = DgCfg<TW>;
-  constexpr int PS = D::PS, IS = D::IS, RS = D::RS, NR = D::NR;
+  constexpr int PS = D::PS, IS = D::IS, RS = D::RS, NR = D::NR, NT = 256;
   extern __shared__ __align__(16) float dg_smem[];
-  float* dys = dg_smem;                                        // [24][PS]
-  float4* wsm = reinterpret_cast<float4*>(dg_smem + kC * PS);  // [tap][ks][nt][lane] (b0 hi, b1 hi, b0 lo, b1 lo)
-  float* bnc = dg_smem + kC * PS + 2 * kC * kC * 9;
+  float* ring = dg_smem;                                        // [stages][24][PS]
+  float4* wsm = reinterpret_cast<float4*>(dg_smem + (WS ? 2 : 1) * D::STAGE);  // [tap][ks][nt][lane] (b0 hi, b1 hi, b0 lo, b1 lo)
+  float* bnc = reinterpret_cast<float*>(wsm) + 2 * kC * kC * 9;
   float* affi = bnc + 8 * kC;                                  // (mean, rstd, scale, shift) x 24 of the producing layer
   float* bnred = affi + 4 * kC;                                // [8 warps][24][2]
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int tid = WS && threadIdx.x >= NT ? threadIdx.x - NT : threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int hin2 = hin * hin, hw = hout * hout;
-  load_bnc(bnc, aff_out, coef, tid);
-  if (tid < 4 * kC) affi[tid] = aff_in[tid];
-  for (int i = tid; i < 8 * 2 * kC; i += 256) bnred[i] = 0.f;
+  load_bnc(bnc, aff_out, coef, threadIdx.x);
+  if (threadIdx.x < 4 * kC) affi[threadIdx.x] = aff_in[threadIdx.x];
+  for (int i = threadIdx.x; i < 8 * 2 * kC; i += blockDim.x) bnred[i] = 0.f;
 
   // B[k = co][n = ci] of (tap, ks, nt): b0 = W[8ks + t][8nt + g][tap], b1 = W[8ks + t + 4][8nt + g][tap]
-  for (int idx = tid; idx < 9 * 3 * 3 * 32; idx += 256) {
+  for (int idx = threadIdx.x; idx < 9 * 3 * 3 * 32; idx += blockDim.x) {
     const int ln = idx & 31, q = idx >> 5;
     const int nt = q % 3, ks = (q / 3) % 3, tap = q / 9;
     const int co = 8 * ks + (ln & 3), ci = 8 * nt + (ln >> 2);
@@ -807,6 +871,7 @@ conv_dgrad_tc_kernel(const float* __restrict__ yout, const float* __restrict__ d
     split_tf32(w[((size_t)(co + 4) * kC + ci) * 9 + tap], h1, l1);
     wsm[idx] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
   }
+  __syncthreads();
 
   int dso[2][2];
 #pragma unroll
@@ -824,10 +889,8 @@ conv_dgrad_tc_kernel(const float* __restrict__ yout, const float* __restrict__ d
   const int s_lane = tid / POS, s_pos = tid - s_lane * POS;
   const int s_r = s_pos / PERROW, s_v = s_pos - s_r * PERROW;
 
-  UnitWalk<D::NIMG, TW, TW> walk(tiles, tiles_x);
-  for (int u = blockIdx.x; u < units; u += gridDim.x, walk.next()) {
-    const UnitPos up = walk.pos();
-    __syncthreads();                       // previous unit consumed (first pass: wsm / bnc visible after the next barrier)
+  auto stage = [&](int st, const UnitPos& up) {
+    float* dys = ring + st * D::STAGE;
     if (s_lane < LANES) {
       const int oh = up.r0 + s_r, ow = up.c0 + (s_v < TW / 4 ? 4 * s_v : TW);
       const bool pv = oh < hout && ow < hout;
@@ -853,8 +916,10 @@ conv_dgrad_tc_kernel(const float* __restrict__ yout, const float* __restrict__ d
         }
       }
     }
-    __syncthreads();
+  };
 
+  auto compute = [&](int st, const UnitPos& up) {
+    const float* dys = ring + st * D::STAGE;
 #pragma unroll 1
     for (int j = 0; j < 2; ++j) {
       const float4* wq = wsm;
@@ -941,14 +1006,16 @@ conv_dgrad_tc_kernel(const float* __restrict__ yout, const float* __restrict__ d
             if (g == 0) bnred[(warp * kC + 8 * nt + 2 * t + e) * 2 + k] += v;
           }
     }
-  }
+  };
+
+  unit_loop<WS, NT>(units, UnitWalk<D::NIMG, TW, TW>(tiles, tiles_x), stage, compute);
 
   __syncthreads();
-  if (tid < 2 * kC) {                        // fixed-order sum over the warps: one partial per block
+  if (threadIdx.x < 2 * kC) {                // fixed-order sum over the consumer warps: one partial per block
     float v = 0.f;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) v += bnred[wv * 2 * kC + tid];
-    bn_part[(size_t)blockIdx.x * 2 * kC + tid] = v;
+    for (int wv = 0; wv < 8; ++wv) v += bnred[wv * 2 * kC + threadIdx.x];
+    bn_part[(size_t)blockIdx.x * 2 * kC + threadIdx.x] = v;
   }
 }
 

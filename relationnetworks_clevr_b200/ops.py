@@ -229,6 +229,10 @@ REL_FLAG_DGRAD_2PASS = 2
 relation_flags = int(os.environ.get("RN_B200_REL_FLAGS", "0"))
 # rn_conv_cfg.flags (RN_CONV_FLAG_*): 1 = fp32 SIMT convolutions everywhere, 2 = tensor-core forward as well (tests, A/B timing)
 conv_flags = int(os.environ.get("RN_B200_CONV_FLAGS", "0"))
+# The tensor-core g-MLP keeps activations as fp16 (hi + lo): a hidden activation above 65504 overflows to inf, which the
+# fp32 reference would survive.  Trained and seeded CLEVR models sit 3 orders of magnitude below that, so the check is
+# opt-in (it costs a device synchronisation per forward): RN_B200_CHECK_FINITE=1 raises instead of returning inf / NaN.
+check_finite = os.environ.get("RN_B200_CHECK_FINITE", "0") == "1"
 
 
 def relation_cfg(B, n, k, Q, G, L, qinj, precision: str, training: bool, flags=None) -> RelationCfg:
@@ -272,6 +276,10 @@ class RelationFunction(torch.autograd.Function):
             check(lib().rn_relation_fwd(C.byref(cfg), x_.data_ptr(), q_.data_ptr(), ptr_array(ws), ptr_array(bs),
                                         xg.data_ptr(), saved.data_ptr(), scratch.data_ptr(), _stream()),
                   "rn_relation_fwd")
+        if check_finite and precision != "fp32" and not torch.cuda.is_current_stream_capturing() \
+                and not bool(torch.isfinite(xg).all()):
+            raise RuntimeError("rn_relation_fwd: non-finite x_g -- a g-layer activation left the fp16 range of the "
+                               "tensor-core path (|h| > 65504) or the inputs are non-finite; use precision='fp32'")
         if training:
             ctx.cfg = cfg
             ctx.saved_buf = saved

@@ -1,4 +1,5 @@
-"""Diagnostics (not a test): a few full training steps at batch 640 (for `ncu --metrics gpu__time_duration.sum` launch lists)."""
+"""Diagnostics (not a test): a few full training steps (argv: steps, config, batch) for `ncu --metrics gpu__time_duration.sum`
+launch lists; profiles/summarize.py `laststep` keeps the launches of the last step."""
 import contextlib, io, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,7 +14,7 @@ with contextlib.redirect_stdout(io.StringIO()):
     m = R.RN(A, hyp)
 m.cuda().train()
 opt = FlatClipAdam(m.parameters())
-B = 640
+B = int(sys.argv[3]) if len(sys.argv) > 3 else 640
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 img = torch.rand(B, 3, 128, 128, device="cuda"); q = torch.randint(1, 83, (B, 20), device="cuda"); lab = torch.randint(0, 28, (B,), device="cuda")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
