@@ -894,25 +894,35 @@ conv_dgrad_tc_kernel(const float* __restrict__ yout, const float* __restrict__ d
     if (s_lane < LANES) {
       const int oh = up.r0 + s_r, ow = up.c0 + (s_v < TW / 4 ? 4 * s_v : TW);
       const bool pv = oh < hout && ow < hout;
-      const int poff = oh * hout + ow;
+      const int poff = pv ? oh * hout + ow : 0;
       float* d = dys + s_r * RS + (s_v < TW / 4 ? 4 * s_v : TW);
+      // every load of the thread in flight before the first use (branch-free: an invalid item reads a valid address and
+      // is masked), then the BatchNorm-backward transform
+      float4 yv[SITER], dv[SITER];
+#pragma unroll
+      for (int i = 0; i < SITER; ++i) {
+        const int pl = min(s_lane + LANES * i, PLANES - 1);
+        const int img = D::NIMG == 1 ? 0 : pl / kC, co = pl - img * kC;
+        const size_t off = ((size_t)min(up.b0 + img, B - 1) * kC + co) * hw + poff;
+        if (s_v < TW / 4) {
+          yv[i] = *reinterpret_cast<const float4*>(yout + off);
+          dv[i] = *reinterpret_cast<const float4*>(dAout + off);
+        } else {
+          yv[i] = make_float4(yout[off], 0.f, 0.f, 0.f);
+          dv[i] = make_float4(dAout[off], 0.f, 0.f, 0.f);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < SITER; ++i) {
         const int pl = s_lane + LANES * i;
         if (pl < PLANES) {
           const int img = D::NIMG == 1 ? 0 : pl / kC, co = pl - img * kC;
           const bool ok = pv && up.b0 + img < B;
-          const size_t off = ((size_t)(up.b0 + img) * kC + co) * hw + poff;
           BnBwdCoef k;
           k.load(bnc, co);
           float* dd = d + co * PS + img * IS;
-          if (s_v < TW / 4) {
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) o = k.apply4(*reinterpret_cast<const float4*>(yout + off), *reinterpret_cast<const float4*>(dAout + off));
-            *reinterpret_cast<float4*>(dd) = o;
-          } else {
-            *dd = ok ? k.apply(yout[off], dAout[off]) : 0.f;
-          }
+          if (s_v < TW / 4) *reinterpret_cast<float4*>(dd) = ok ? k.apply4(yv[i], dv[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          else *dd = ok ? k.apply(yv[i].x, dv[i].x) : 0.f;
         }
       }
     }
