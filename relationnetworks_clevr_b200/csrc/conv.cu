@@ -11,6 +11,7 @@
 #include "sgemm.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace rn {
 
@@ -689,6 +690,12 @@ namespace rn {
 // ---- tensor-core path (conv_tc.cuh): side % 64 == 0 keeps every layer's rows float4-aligned -------------------------
 static bool conv_tc_ok(const rn_conv_cfg& c) { return c.side % 64 == 0 && !(c.flags & RN_CONV_FLAG_SIMT); }
 
+// units per SM from which the 24 -> 24 backward kernels use the warp-specialised ring (diagnostic override: RN_B200_CONV_WS_MIN)
+static int conv_ws_min_units() {
+  static const int v = []() { const char* e = getenv("RN_B200_CONV_WS_MIN"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
 struct TcGrid {
   int tw, tiles_x, tiles, units, grid;
 };
@@ -893,12 +900,21 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
         ctc::conv_wgrad3_tc_kernel<false, false><<<g.grid, 256, smem, st>>>(in, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
       }
     } else if (tc) {
-      if (hout > 8) {
+      // warp-specialised ring (one block per SM) when every SM gets several units; otherwise two single-stage blocks per
+      // SM, which split a short unit list more evenly (80 images: 3 units per block leave a quarter of the SMs idle)
+      const bool ws = hout > 8 && (long long)cfg->B * cdiv(hout, 16) * cdiv(hout, 8) >= (long long)conv_ws_min_units() * sm_count();
+      if (ws) {
         const TcGrid g = tc_grid(cfg->B, hout, 8, 2, 1);
         nblk = g.grid;
         const size_t smem = ctc::WgCfg<16>::smem(true);
         RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctc::conv_wgrad_tc_kernel<16, true><<<g.grid, 448, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+      } else if (hout > 8) {
+        const TcGrid g = tc_grid(cfg->B, hout, 8, 2, 2);
+        nblk = g.grid;
+        const size_t smem = ctc::WgCfg<16>::smem(false);
+        RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctc::conv_wgrad_tc_kernel<16, false><<<g.grid, 224, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
       } else {
         const TcGrid g = tc_grid(cfg->B, hout, 8, 2, 2);
         nblk = g.grid;
@@ -942,15 +958,22 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
       const int qt = cdiv(hout, kTile);
       // reads (y_l, dA_l), writes dA_{l-1} into the other buffer
       if (tc) {
-        const TcGrid g = tc_grid(cfg->B, hout, 16, 4, hout > 8 ? 1 : 2);
-        if (g.tw == 16) {
+        const bool ws = hout > 8 && (long long)cfg->B * cdiv(hout, 16) * cdiv(hout, 16) >= (long long)conv_ws_min_units() * sm_count();
+        const TcGrid g = tc_grid(cfg->B, hout, 16, 4, ws ? 1 : 2);
+        const float* y_in = saved + p.y_off[l - 1];
+        const float* aff_in = saved + p.aff_off[l - 1];
+        if (ws) {
           const size_t smem = ctc::DgCfg<16>::smem(true);
           RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          ctc::conv_dgrad_tc_kernel<16, true><<<g.grid, 512, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, saved + p.y_off[l - 1], saved + p.aff_off[l - 1], bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+          ctc::conv_dgrad_tc_kernel<16, true><<<g.grid, 512, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, y_in, aff_in, bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+        } else if (g.tw == 16) {
+          const size_t smem = ctc::DgCfg<16>::smem(false);
+          RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          ctc::conv_dgrad_tc_kernel<16, false><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, y_in, aff_in, bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
         } else {
           const size_t smem = ctc::DgCfg<8>::smem(false);
           RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          ctc::conv_dgrad_tc_kernel<8, false><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, saved + p.y_off[l - 1], saved + p.aff_off[l - 1], bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
+          ctc::conv_dgrad_tc_kernel<8, false><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, y_in, aff_in, bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
         }
         bn_blocks = g.grid;
       } else {
