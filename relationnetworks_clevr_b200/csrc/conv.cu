@@ -690,12 +690,6 @@ namespace rn {
 // ---- tensor-core path (conv_tc.cuh): side % 64 == 0 keeps every layer's rows float4-aligned -------------------------
 static bool conv_tc_ok(const rn_conv_cfg& c) { return c.side % 64 == 0 && !(c.flags & RN_CONV_FLAG_SIMT); }
 
-// units per SM from which the 24 -> 24 backward kernels use the warp-specialised ring (diagnostic override: RN_B200_CONV_WS_MIN)
-static int conv_ws_min_units() {
-  static const int v = []() { const char* e = getenv("RN_B200_CONV_WS_MIN"); return e ? atoi(e) : 0; }();
-  return v;
-}
-
 struct TcGrid {
   int tw, tiles_x, tiles, units, grid;
 };
@@ -900,21 +894,14 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
         ctc::conv_wgrad3_tc_kernel<false, false><<<g.grid, 256, smem, st>>>(in, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
       }
     } else if (tc) {
-      // warp-specialised ring (one block per SM) when every SM gets several units; otherwise two single-stage blocks per
-      // SM, which split a short unit list more evenly (80 images: 3 units per block leave a quarter of the SMs idle)
-      const bool ws = hout > 8 && (long long)cfg->B * cdiv(hout, 16) * cdiv(hout, 8) >= (long long)conv_ws_min_units() * sm_count();
-      if (ws) {
+      // 32x32 / 16x16 outputs: warp-specialised ring, one block per SM (measured faster than two single-stage blocks per
+      // SM at every batch from 80 to 640); 8x8 outputs: single-stage form
+      if (hout > 8) {
         const TcGrid g = tc_grid(cfg->B, hout, 8, 2, 1);
         nblk = g.grid;
         const size_t smem = ctc::WgCfg<16>::smem(true);
         RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctc::conv_wgrad_tc_kernel<16, true><<<g.grid, 448, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
-      } else if (hout > 8) {
-        const TcGrid g = tc_grid(cfg->B, hout, 8, 2, 2);
-        nblk = g.grid;
-        const size_t smem = ctc::WgCfg<16>::smem(false);
-        RN_CUDA(cudaFuncSetAttribute(ctc::conv_wgrad_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctc::conv_wgrad_tc_kernel<16, false><<<g.grid, 224, smem, st>>>(in, in_aff, y, dA, aff, coef, wpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
       } else {
         const TcGrid g = tc_grid(cfg->B, hout, 8, 2, 2);
         nblk = g.grid;
@@ -958,7 +945,7 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
       const int qt = cdiv(hout, kTile);
       // reads (y_l, dA_l), writes dA_{l-1} into the other buffer
       if (tc) {
-        const bool ws = hout > 8 && (long long)cfg->B * cdiv(hout, 16) * cdiv(hout, 16) >= (long long)conv_ws_min_units() * sm_count();
+        const bool ws = hout > 8;
         const TcGrid g = tc_grid(cfg->B, hout, 16, 4, ws ? 1 : 2);
         const float* y_in = saved + p.y_off[l - 1];
         const float* aff_in = saved + p.aff_off[l - 1];
@@ -966,10 +953,6 @@ extern "C" int rn_conv_bwd(const rn_conv_cfg* cfg, const void* img_any, const fl
           const size_t smem = ctc::DgCfg<16>::smem(true);
           RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           ctc::conv_dgrad_tc_kernel<16, true><<<g.grid, 512, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, y_in, aff_in, bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
-        } else if (g.tw == 16) {
-          const size_t smem = ctc::DgCfg<16>::smem(false);
-          RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          ctc::conv_dgrad_tc_kernel<16, false><<<g.grid, 256, smem, st>>>(y, dA, aff, coef, L[l].w, dA_next, y_in, aff_in, bnpart, cfg->B, hin, hout, g.tiles_x, g.tiles, g.units);
         } else {
           const size_t smem = ctc::DgCfg<8>::smem(false);
           RN_CUDA(cudaFuncSetAttribute(ctc::conv_dgrad_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
