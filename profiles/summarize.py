@@ -50,6 +50,39 @@ def full(path):
                 print(f"   {h:85s} {units[i]:12s} {r[i]}")
 
 
+def steprows(path):
+    """One line per kernel of a `--set full` capture of one training step (profiles/r02*_step_b640_ncu_full.txt)."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+
+    def val(r, k):
+        return float(r[col[k]].replace(",", "") or 0)
+
+    print("# columns: kernel | time ms | tensor pipe % | DRAM read GB | DRAM write GB | DRAM % of peak | achieved DRAM GB/s (vs 6553 measured copy)"
+          " | L2 % | issue active % | regs | grid x block")
+    tot = 0.0
+    for r in rows[2:]:
+        t = val(r, "gpu__time_duration.sum") * tscale[units[col["gpu__time_duration.sum"]]]
+        rd = val(r, "dram__bytes_read.sum") * scale[units[col["dram__bytes_read.sum"]]] / 1e9
+        wr = val(r, "dram__bytes_write.sum") * scale[units[col["dram__bytes_write.sum"]]] / 1e9
+        name = r[col["Kernel Name"]].split("(")[0].replace("rn::", "")
+        tot += t
+        print(f"{name[:44]:44s} {t:6.3f} ms  tensor {val(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'):5.1f}%"
+              f"  rd {rd:6.3f} GB  wr {wr:6.3f} GB  dram {val(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):5.1f}%"
+              f"  {(rd + wr) / (t / 1e3) if t else 0:7.0f} GB/s  L2 {val(r, 'lts__throughput.avg.pct_of_peak_sustained_elapsed'):5.1f}%"
+              f"  issue {val(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active') if 'smsp__issue_active.avg.pct_of_peak_sustained_active' in col else float('nan'):5.1f}%"
+              f"  regs {int(val(r, 'launch__registers_per_thread'))}  {int(val(r, 'launch__grid_size'))}x{int(val(r, 'launch__block_size'))}")
+    print(f"# {len(rows) - 2} kernels, {tot:.3f} ms serialised")
+
+
+if __name__ == "__main__" and sys.argv[1] == "steprows":
+    steprows(sys.argv[2])
+    sys.exit(0)
+
 if __name__ == "__main__" and sys.argv[1] == "laststep":
     launches(sys.argv[2], int(sys.argv[3]))
     sys.exit(0)
