@@ -228,17 +228,24 @@ lstm_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ act, con
   }
 }
 
-// dP[v, r] = sum over positions p = t * B + s with tokens[s, t] == v of dG[p, r], in position order within 16 fixed
-// slices (deterministic).  grid = V, 512 threads.  list: dynamic shared memory, 16 slices x `slice` entries.
+// dP[v, r] = sum over positions p = t * B + s with tokens[s, t] == v of dG[p, r].  Two levels, both in a fixed order
+// (deterministic, no atomics, no sort): block (v, sl) of lstm_dp_kernel takes slice sl of kDpSlices equal slices of the
+// positions -- its 16 warps compact the hits of 16 sub-slices into shared-memory lists, then thread r sums column r of the
+// listed rows -- and lstm_dp_reduce_kernel adds the kDpSlices partials.  One block per word (the first version) is a
+// performance cliff on real questions: the padding word holds a third of all positions, and its block summed thousands of
+// rows as one chain of dependent loads.
+constexpr int kDpSlices = 16;
+
 __global__ void __launch_bounds__(kLG)
-lstm_dp_kernel(const long long* __restrict__ tokens, const float* __restrict__ dG, int B, int T, int V, int slice,
-               float* __restrict__ dP) {
-  extern __shared__ int dp_list[];
+lstm_dp_kernel(const long long* __restrict__ tokens, const float* __restrict__ dG, int B, int T, int V, int slice, int sub,
+               float* __restrict__ part) {
+  extern __shared__ int dp_list[];              // [16 warps][sub]
   __shared__ int counts[16];
-  const int v = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.x, sl = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = B * T;
   int cnt = 0;
-  const int p_begin = warp * slice, p_end = min(n, p_begin + slice);
+  const int s_end = min(n, (sl + 1) * slice);
+  const int p_begin = sl * slice + warp * sub, p_end = min(s_end, p_begin + sub);
   for (int base = p_begin; base < p_end; base += 32) {
     const int p = base + lane;
     bool hit = false;
@@ -249,7 +256,7 @@ lstm_dp_kernel(const long long* __restrict__ tokens, const float* __restrict__ d
       hit = (int)tk == v;
     }
     const uint32_t m = __ballot_sync(0xffffffffu, hit);
-    if (hit) dp_list[warp * slice + cnt + __popc(m & ((1u << lane) - 1u))] = p;
+    if (hit) dp_list[warp * sub + cnt + __popc(m & ((1u << lane) - 1u))] = p;
     cnt += __popc(m);
   }
   if (lane == 0) counts[warp] = cnt;
@@ -258,39 +265,69 @@ lstm_dp_kernel(const long long* __restrict__ tokens, const float* __restrict__ d
   float acc = 0.f;
   for (int wv = 0; wv < 16; ++wv) {
     const int c = counts[wv];
-    const int* l = dp_list + wv * slice;
+    const int* l = dp_list + wv * sub;
     int i = 0;
-    for (; i + 4 <= c; i += 4) {
-      const float x0 = dG[(size_t)l[i] * kLG + r], x1 = dG[(size_t)l[i + 1] * kLG + r];
-      const float x2 = dG[(size_t)l[i + 2] * kLG + r], x3 = dG[(size_t)l[i + 3] * kLG + r];
-      acc += (x0 + x1) + (x2 + x3);
+    for (; i + 8 <= c; i += 8) {
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = dG[(size_t)l[i + u] * kLG + r];
+      acc += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
     }
     for (; i < c; ++i) acc += dG[(size_t)l[i] * kLG + r];
   }
+  part[((size_t)v * kDpSlices + sl) * kLG + r] = acc;
+}
+
+__global__ void __launch_bounds__(kLG) lstm_dp_reduce_kernel(const float* __restrict__ part, float* __restrict__ dP) {
+  const int v = blockIdx.x, r = threadIdx.x;
+  float x[kDpSlices];
+#pragma unroll
+  for (int sl = 0; sl < kDpSlices; ++sl) x[sl] = part[((size_t)v * kDpSlices + sl) * kLG + r];
+  float acc = 0.f;
+#pragma unroll
+  for (int sl = 0; sl < kDpSlices; ++sl) acc += x[sl];
   dP[(size_t)v * kLG + r] = acc;
 }
 
 // blocks [0, 512): dW_ih[r, :] = sum_v dP[v, r] emb[v, :], db_ih[r] = db_hh[r] = sum_v dP[v, r];
-// blocks [512, 512 + V): demb[v, :] = sum_r dP[v, r] W_ih[r, :].   E threads.
-__global__ void lstm_param_grad_kernel(const float* __restrict__ dP, const float* __restrict__ emb, const float* __restrict__ w_ih,
-                                       int V, int E, float* __restrict__ dw_ih, float* __restrict__ db_ih,
-                                       float* __restrict__ db_hh, float* __restrict__ demb) {
-  const int e = threadIdx.x;
-  if ((int)blockIdx.x < kLG) {
-    const int r = blockIdx.x;
-    float acc = 0.f, bsum = 0.f;
-    for (int v = 0; v < V; ++v) {
-      const float d = dP[(size_t)v * kLG + r];
-      acc = fmaf(d, emb[(size_t)v * E + e], acc);
-      bsum += d;
+// blocks [512, 512 + V): demb[v, :] = sum_r dP[v, r] W_ih[r, :].   256 threads: thread = (column e, part) with 256 / E parts
+// that split the sum (a 512-term chain of dependent L2 loads per thread took 29 us with E threads per block); the parts
+// are combined in shared memory in a fixed order.
+__global__ void __launch_bounds__(256)
+lstm_param_grad_kernel(const float* __restrict__ dP, const float* __restrict__ emb, const float* __restrict__ w_ih, int V, int E,
+                       float* __restrict__ dw_ih, float* __restrict__ db_ih, float* __restrict__ db_hh,
+                       float* __restrict__ demb) {
+  __shared__ float red[256], redb[256];
+  const int parts = 256 / E, e = threadIdx.x % E, part = threadIdx.x / E;
+  const bool active = part < parts;
+  float acc = 0.f, bsum = 0.f;
+  const bool row_block = (int)blockIdx.x < kLG;
+  if (active) {
+    if (row_block) {
+      const int r = blockIdx.x;
+      for (int v = part; v < V; v += parts) {
+        const float d = dP[(size_t)v * kLG + r];
+        acc = fmaf(d, emb[(size_t)v * E + e], acc);
+        bsum += d;
+      }
+    } else {
+      const int v = blockIdx.x - kLG;
+#pragma unroll 4
+      for (int r = part; r < kLG; r += parts) acc = fmaf(dP[(size_t)v * kLG + r], w_ih[(size_t)r * E + e], acc);
     }
-    dw_ih[(size_t)r * E + e] = acc;
-    if (e == 0) { db_ih[r] = bsum; db_hh[r] = bsum; }
-  } else {
-    const int v = blockIdx.x - kLG;
-    float acc = 0.f;
-    for (int r = 0; r < kLG; ++r) acc = fmaf(dP[(size_t)v * kLG + r], w_ih[(size_t)r * E + e], acc);
-    demb[(size_t)v * E + e] = acc;
+  }
+  red[threadIdx.x] = acc;
+  redb[threadIdx.x] = bsum;
+  __syncthreads();
+  if (part == 0) {
+    float a = 0.f, bs = 0.f;
+    for (int q = 0; q < parts; ++q) { a += red[q * E + e]; bs += redb[q * E + e]; }
+    if (row_block) {
+      dw_ih[(size_t)blockIdx.x * E + e] = a;
+      if (e == 0) { db_ih[blockIdx.x] = bs; db_hh[blockIdx.x] = bs; }
+    } else {
+      demb[(size_t)(blockIdx.x - kLG) * E + e] = a;
+    }
   }
 }
 
@@ -338,7 +375,8 @@ extern "C" int rn_lstm_workspace(const rn_lstm_cfg* cfg, size_t* saved_floats, s
   if (!lstm_ok(cfg)) return fail(RN_ERR_UNSUPPORTED, "rn_lstm_*: needs H == 128, 1 <= T <= 64 (H=%d T=%d)", cfg->H, cfg->T);
   const size_t tb = (size_t)cfg->T * cfg->B;
   *saved_floats = round_up((size_t)cfg->V * kLG, 64) + (cfg->training ? tb * (kLG + 2 * kLH) : 0);
-  *scratch_floats = cfg->training ? tb * kLG + round_up((size_t)cfg->V * kLG, 64) + lstm_splitk_floats() : 64;
+  *scratch_floats = cfg->training ? tb * kLG + round_up((size_t)cfg->V * kLG, 64) + lstm_splitk_floats() +
+                                        (size_t)cfg->V * kDpSlices * kLG : 64;
   return RN_OK;
 }
 
@@ -392,14 +430,18 @@ extern "C" int rn_lstm_bwd(const rn_lstm_cfg* cfg, const int64_t* tokens, const 
     RN_CUDA(cudaMemsetAsync(dw_hh, 0, sizeof(float) * kLG * kLH, st));
   }
   // table gradient, then the embedding / W_ih / bias gradients
-  int slice = cdiv((long long)tb, 16);
-  slice = (slice + 31) / 32 * 32;
-  const size_t list_bytes = (size_t)16 * slice * sizeof(int);
-  RN_CHECK_ARG(list_bytes <= 200 * 1024, "rn_lstm_bwd: T*B = %zu exceeds the position-list capacity (51200)", tb);
+  float* dp_part = ws + lstm_splitk_floats();                 // [V][kDpSlices][512]
+  const int slice = cdiv((long long)tb, kDpSlices);
+  const int sub = (cdiv(slice, 16) + 31) / 32 * 32;           // positions per warp, a multiple of the warp size
+  const size_t list_bytes = (size_t)16 * sub * sizeof(int);
+  RN_CHECK_ARG(list_bytes <= 200 * 1024, "rn_lstm_bwd: T*B = %zu exceeds the position-list capacity", tb);
   RN_CUDA(cudaFuncSetAttribute(lstm_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)list_bytes));
-  lstm_dp_kernel<<<V, kLG, list_bytes, st>>>(reinterpret_cast<const long long*>(tokens), dG, B, T, V, slice, dP);
+  lstm_dp_kernel<<<dim3(V, kDpSlices), kLG, list_bytes, st>>>(reinterpret_cast<const long long*>(tokens), dG, B, T, V, slice, sub,
+                                                               dp_part);
   RN_LAUNCH_CHECK("lstm_dp_kernel");
-  lstm_param_grad_kernel<<<kLG + V, E, 0, st>>>(dP, emb, w_ih, V, E, dw_ih, db_ih, db_hh, demb);
+  lstm_dp_reduce_kernel<<<V, kLG, 0, st>>>(dp_part, dP);
+  RN_LAUNCH_CHECK("lstm_dp_reduce_kernel");
+  lstm_param_grad_kernel<<<kLG + V, 256, 0, st>>>(dP, emb, w_ih, V, E, dw_ih, db_ih, db_hh, demb);
   RN_LAUNCH_CHECK("lstm_param_grad_kernel");
   return RN_OK;
 }
