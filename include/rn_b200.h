@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RN_ABI_VERSION 2
+#define RN_ABI_VERSION 3
 
 /* error codes */
 #define RN_OK 0
@@ -71,6 +71,10 @@ const char* rn_last_error(void);
 
 /* Number of kernels this library has launched in the calling process (monotonic; for bench accounting). */
 unsigned long long rn_launch_count(void);
+/* sizeof of the seven structs of this header as the library was compiled, in declaration order (rn_relation_cfg, rn_f_cfg,
+ * rn_conv_cfg, rn_conv_layer, rn_conv_grads, rn_lstm_cfg, rn_adam_cfg): a binding checks its own mirrors against them once at
+ * load time (a stale mirror would otherwise be read as garbage fields).  Returns the number of entries written (<= n). */
+int rn_abi_struct_sizes(int32_t* out, int n);
 
 /* Returns RN_OK when `device` is a compute-capability 10.x GPU, RN_ERR_ARCH otherwise. */
 int rn_device_check(int device);

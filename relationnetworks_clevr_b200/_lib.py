@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librn_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-RN_ABI_VERSION = 2
+RN_ABI_VERSION = 3
 PRECISION = {"fp32": 0, "parity": 1, "fast": 2}
 MAX_G_LAYERS = 8
 
@@ -57,6 +57,7 @@ SIGNATURES = {
     "rn_abi_version": (C.c_int, []),
     "rn_last_error": (C.c_char_p, []),
     "rn_launch_count": (C.c_ulonglong, []),
+    "rn_abi_struct_sizes": (C.c_int, [C.POINTER(C.c_int32), C.c_int]),
     "rn_device_check": (C.c_int, [C.c_int]),
     "rn_relation_tc_supported": (C.c_int, [C.POINTER(RelationCfg)]),
     "rn_relation_workspace": (C.c_int, [C.POINTER(RelationCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
@@ -110,6 +111,12 @@ def lib() -> C.CDLL:
                     fn.argtypes = args
                 if handle.rn_abi_version() != RN_ABI_VERSION:
                     raise RuntimeError("librn_b200.so ABI version mismatch; rebuild it")
+                mirrors = (RelationCfg, FCfg, ConvCfg, ConvLayer, ConvGrads, LstmCfg, AdamCfg)
+                sizes = (C.c_int32 * len(mirrors))()
+                n = handle.rn_abi_struct_sizes(sizes, len(mirrors))
+                bad = [m.__name__ for m, sz in zip(mirrors, sizes) if C.sizeof(m) != sz]
+                if n != len(mirrors) or bad:
+                    raise RuntimeError(f"ctypes mirrors out of date with include/rn_b200.h: {bad or n}")
                 _lib = handle
     return _lib
 

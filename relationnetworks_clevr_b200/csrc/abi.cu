@@ -43,6 +43,15 @@ extern "C" const char* rn_last_error(void) { return rn::error_buffer(); }
 namespace rn { unsigned long long launch_count(); }
 extern "C" unsigned long long rn_launch_count(void) { return rn::launch_count(); }
 
+extern "C" int rn_abi_struct_sizes(int32_t* out, int n) {
+  const int32_t sizes[] = {(int32_t)sizeof(rn_relation_cfg), (int32_t)sizeof(rn_f_cfg),       (int32_t)sizeof(rn_conv_cfg),
+                           (int32_t)sizeof(rn_conv_layer),   (int32_t)sizeof(rn_conv_grads),  (int32_t)sizeof(rn_lstm_cfg),
+                           (int32_t)sizeof(rn_adam_cfg)};
+  int i = 0;
+  for (; out != nullptr && i < n && i < (int)(sizeof(sizes) / sizeof(sizes[0])); ++i) out[i] = sizes[i];
+  return i;
+}
+
 extern "C" int rn_device_check(int device) {
   int major = 0, minor = 0;
   RN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));

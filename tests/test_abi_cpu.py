@@ -32,6 +32,16 @@ def test_header_symbols_are_exported(lib):
     assert lib.rn_abi_version() == _lib.RN_ABI_VERSION == int(re.search(r"#define RN_ABI_VERSION (\d+)", header).group(1))
 
 
+def test_struct_mirrors_match_the_compiled_header(lib):
+    """The ctypes mirrors of the seven header structs have the sizes the library was compiled with (checked at load time
+    too: a stale mirror would be read as garbage fields, e.g. rn_conv_cfg.flags)."""
+    mirrors = (_lib.RelationCfg, _lib.FCfg, _lib.ConvCfg, _lib.ConvLayer, _lib.ConvGrads, _lib.LstmCfg, _lib.AdamCfg)
+    sizes = (C.c_int32 * 8)()
+    assert lib.rn_abi_struct_sizes(sizes, 8) == len(mirrors)
+    assert [C.sizeof(m) for m in mirrors] == list(sizes)[:len(mirrors)]
+    assert lib.rn_abi_struct_sizes(sizes, 3) == 3 and lib.rn_abi_struct_sizes(None, 3) == 0
+
+
 def test_argument_validation_without_gpu(lib):
     a, b = C.c_size_t(), C.c_size_t()
     bad = _lib.RelationCfg(4, 64, 26, 128, 255, 4, 0, 0, 1)      # G not a multiple of 4
